@@ -1,0 +1,218 @@
+/*
+ * dra_alloc.h — C ABI of libdra_alloc.so, the B200 (sm_100a) allocation hot path.
+ *
+ * This is the drop-in boundary for ONE path of NVIDIA/k8s-dra-driver: the per-node GPU/MIG claim search
+ * behind the classic-DRA controller surface  Allocate() / UnsuitableNodes() / Deallocate()  that
+ * BASELINE.json's north_star names.  That surface is ABSENT from the reference snapshot
+ * (cmd/nvidia-dra-controller/ holds only main.go, imex.go, types.go — SURVEY.md F1); each entry point
+ * below cites the reference interface it stands in for or the reference code that fixes its semantics.
+ * A Go driver binds these with cgo (INTEGRATION.md shows the stub); tests bind them with ctypes.
+ *
+ * Plain C: pointers + sizes, caller-owned buffers, int return codes, no callbacks, no torch types.
+ * Semantics are normative in spec/ALLOCATION.md; oracle/ is the CPU checker, never linked here.
+ *
+ * Threading: one in-flight call per dra_ctx (the reference serialises the same way with a global mutex,
+ * cmd/nvidia-dra-plugin/driver.go:119-120, device_state.go:129-130).  Distinct contexts are independent.
+ */
+#ifndef DRA_ALLOC_H
+#define DRA_ALLOC_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRA_ABI_VERSION      1u
+
+#define DRA_MAX_GPUS_PER_NODE 32u   /* one warp lane per GPU of a node */
+#define DRA_MAX_MODELS        16u
+#define DRA_MAX_PROFILES      16u   /* NVML GPU_INSTANCE_PROFILE_COUNT is 10 (go-nvml const.go:764-765) */
+#define DRA_MAX_COUNT         32u   /* devices per GPU claim; k8s caps results per claim at 32
+                                       (vendor/k8s.io/api/resource/v1beta1/types.go:792) */
+#define DRA_MAX_GROUP         32u   /* members of one co-location run (same cap) */
+#define DRA_GPU_NONE          0xFFFFFFFFu
+
+/* ---- records (spec/ALLOCATION.md §1) ------------------------------------------------------------ */
+
+/* One physical GPU.  Mirrors the fields of GpuInfo that matter to allocation
+ * (cmd/nvidia-dra-plugin/deviceinfo.go:30-43: index, migEnabled, memoryBytes) plus the occupancy the
+ * removed NodeAllocationState CRD carried.  busy bit i = memory slice i in use
+ * (deviceinfo.go:199-204, go-nvml nvml.h:9761-9765). */
+typedef struct dra_gpu_rec {
+    uint16_t busy;
+    uint8_t  flags;         /* DRA_GPU_* */
+    uint8_t  model;         /* row of the placement table */
+    uint32_t mem_free_mib;  /* shareable memory left (SHARED claims) */
+    uint32_t node;          /* owning node index */
+    uint16_t share_cnt;     /* SHARED claims currently on this GPU */
+    uint16_t rsvd;
+} dra_gpu_rec;
+
+#define DRA_GPU_MIG_ENABLED    0x01u  /* nvlib.go:152 / :316-318 — full GPU xor MIG parent */
+#define DRA_GPU_FULL_ALLOCATED 0x02u
+#define DRA_GPU_UNAVAILABLE    0x04u
+
+/* One request.  Flat form of the legacy GpuClaimParameters / MigDeviceClaimParameters
+ * (shapes survive only in demo/specs/mig+mps/sharing-demo-parameters.yaml:22-41 and
+ * demo/specs/selectors/parameters.yaml:7-27) and of today's DeviceRequest + DeviceClass + CEL
+ * `profile == '...'` + matchAttribute parentUUID (demo/specs/quickstart/gpu-test4.yaml:19-44). */
+typedef struct dra_claim_rec {
+    uint8_t  kind;          /* DRA_KIND_* */
+    uint8_t  profile;       /* NVML GI profile enum (kind MIG) */
+    uint16_t count;         /* devices wanted (kind GPU), else ignored */
+    uint32_t node;          /* selectedNode (Allocate) — overridden per candidate in UnsuitableNodes */
+    uint32_t mem_limit_mib; /* kind SHARED: MPS pinned-memory limit, sharing.go:234-237 arithmetic */
+    uint32_t group;         /* != 0: consecutive MIG claims with equal group share one parent GPU */
+} dra_claim_rec;
+
+#define DRA_KIND_GPU    0u
+#define DRA_KIND_MIG    1u
+#define DRA_KIND_SHARED 2u
+
+/* One allocated device (or one failed slot).  Bijective with the reference's device names
+ * gpu-<index> / gpu-<parent>-mig-<profileId>-<start>-<size> (deviceinfo.go:74-80) that
+ * DeviceRequestAllocationResult.Device carries (k8s types.go:795-840). */
+typedef struct dra_out_rec {
+    uint32_t gpu;           /* global inventory index, DRA_GPU_NONE when not allocated */
+    uint8_t  start;
+    uint8_t  size;
+    uint8_t  profile;       /* MIG: claim profile; 0xFF GPU; 0xFE SHARED */
+    uint8_t  status;        /* DRA_ST_* */
+} dra_out_rec;
+
+#define DRA_PROFILE_GPU    0xFFu
+#define DRA_PROFILE_SHARED 0xFEu
+
+#define DRA_ST_OK          0u
+#define DRA_ST_NO_CAPACITY 1u
+#define DRA_ST_BAD_PROFILE 2u
+#define DRA_ST_GROUP       3u
+#define DRA_ST_MEM_LIMIT   4u
+#define DRA_ST_INVALID     5u
+
+/* One (model, profile) cell of the placement table: what getGpuInfo() collects from
+ * GetGpuInstanceProfileInfo + GetGpuInstancePossiblePlacements (nvlib.go:244-295). */
+typedef struct dra_prof_ent {
+    uint8_t  size;          /* memory slices */
+    uint8_t  rsvd;
+    uint16_t start_mask;    /* bit s: placement {start s, size} is possible; 0 = profile not offered */
+} dra_prof_ent;
+
+typedef struct dra_profile_tbl {
+    dra_prof_ent ent[DRA_MAX_PROFILES];
+} dra_profile_tbl;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+
+typedef struct dra_ctx dra_ctx;
+
+typedef struct dra_cfg {
+    uint32_t abi_version;   /* DRA_ABI_VERSION */
+    int32_t  device;        /* CUDA device ordinal */
+    void*    stream;        /* cudaStream_t to run on; NULL = the context creates its own */
+    uint32_t max_claims;    /* capacity hint; buffers grow on demand */
+    uint32_t flags;         /* DRA_CFG_* */
+} dra_cfg;
+
+#define DRA_CFG_USE_GRAPH  0x1u  /* replay the kernel chain as one CUDA graph (host-buffer calls) */
+
+/* error codes (negative) */
+#define DRA_OK        0
+#define DRA_E_INVAL  (-1)
+#define DRA_E_CUDA   (-2)
+#define DRA_E_NCCL   (-3)
+#define DRA_E_NOMEM  (-4)
+#define DRA_E_STATE  (-5)
+
+/* batch flags */
+#define DRA_F_NODE_SORTED 0x1u  /* claims already grouped by ascending node (stable): skip bucketing.
+                                   Verified on the device; violation -> DRA_E_INVAL, nothing changed */
+#define DRA_F_FRESH_INVENTORY 0x2u  /* evaluate against the inventory as dra_set_inventory last loaded it
+                                   (ignoring earlier batches); the result becomes the live inventory */
+
+int  dra_abi_version(void);
+
+/* Creates a context bound to one CUDA device + one stream.  Fails with DRA_E_CUDA when no usable
+ * sm_100 device exists — there is no CPU fallback. */
+int  dra_ctx_create(const dra_cfg* cfg, dra_ctx** out);
+void dra_ctx_destroy(dra_ctx* ctx);
+const char* dra_last_error(const dra_ctx* ctx);      /* ctx may be NULL: last create error */
+
+/* Placement table for one GPU model — replaces the per-GPU migProfiles list built by
+ * deviceLib.getGpuInfo (cmd/nvidia-dra-plugin/nvlib.go:244-295). */
+int  dra_set_placement_table(dra_ctx* ctx, uint32_t model, const dra_profile_tbl* tbl);
+
+/* Inventory of every node this context serves — replaces the AllocatableDevices map published per node
+ * (cmd/nvidia-dra-plugin/nvlib.go:111-180, driver.go:71-83) / the per-node NodeAllocationState CRD of
+ * the classic driver.  gpus sorted by (node, local index); node_off has n_node+1 entries. Copied. */
+int  dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu,
+                       const uint32_t* node_off, uint32_t n_node);
+/* Read the live inventory back (n_gpu records). */
+int  dra_get_inventory(dra_ctx* ctx, dra_gpu_rec* gpus, uint32_t n_gpu);
+/* Restore the live inventory to what dra_set_inventory last loaded (device-side copy). */
+int  dra_reset_inventory(dra_ctx* ctx);
+
+/* Allocate(): stands in for  controller.Driver.Allocate(ctx, claims []*ClaimAllocation, selectedNode)
+ * (k8s.io/dynamic-resource-allocation/controller, not vendored: vendor/modules.txt:757-760) batched over
+ * many pods — every claim carries its selectedNode.  Mutates the context's inventory.
+ *   claims[n_claim]           host memory
+ *   out_off[n_claim] or NULL  first OutRec slot of each claim (NULL: slot i, all counts must be 1)
+ *   out[n_out]                host memory, filled in input order
+ * Per-claim failure is NOT an error (out[].status != 0), like the per-claim Error strings of
+ * cmd/nvidia-dra-plugin/driver.go:126-137. */
+int  dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim,
+                        const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, uint32_t flags);
+
+/* Same, all pointers are DEVICE memory on ctx's device; enqueued on ctx's stream, returns without
+ * synchronising (errors detected on the device surface at the next dra_ctx_sync). */
+int  dra_allocate_batch_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim,
+                               const uint32_t* d_out_off, dra_out_rec* d_out, uint32_t n_out,
+                               uint32_t flags);
+int  dra_ctx_sync(dra_ctx* ctx);
+
+/* UnsuitableNodes(): stands in for  controller.Driver.UnsuitableNodes(ctx, pod, claims, potentialNodes)
+ * batched over pods.  Pure: evaluates each pod's claims on a snapshot of each candidate node.
+ *   pod_off[n_pod+1]   claim range of each pod
+ *   cand_off[n_pod+1]  range of each pod's candidates in cand_nodes
+ *   suitable_bits      ceil(cand_off[n_pod]/8) bytes; bit k = k-th (pod,candidate) pair is suitable */
+int  dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim,
+                          const uint32_t* pod_off, uint32_t n_pod,
+                          const uint32_t* cand_nodes, const uint32_t* cand_off,
+                          uint8_t* suitable_bits);
+
+/* Deallocate(): stands in for controller.Driver.Deallocate(ctx, claim).  Inverse update from the
+ * claims and the OutRecs dra_allocate_batch produced for them (same out_off convention). */
+int  dra_deallocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim,
+                          const uint32_t* out_off, const dra_out_rec* out, uint32_t n_out);
+
+/* ---- multi-GPU (one process per GPU; nodes are sharded whole) ------------------------------------ */
+
+/* 128-byte NCCL unique id, generated on rank 0 and handed to the other ranks by the host runtime. */
+int  dra_comm_unique_id(void* id128);
+int  dra_comm_init(dra_ctx* ctx, const void* id128, int rank, int world);
+/* dra_allocate_batch_device on this rank's claims, then ONE ncclAllGather of n_per_rank OutRecs per rank
+ * into d_out_all[world * n_per_rank] on the same stream (slots past this rank's n_out are zero-filled). */
+int  dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim,
+                                      const uint32_t* d_out_off, dra_out_rec* d_out_all,
+                                      uint32_t n_out, uint32_t n_per_rank, uint32_t flags);
+
+/* ---- host memory + instrumentation ---------------------------------------------------------------- */
+
+/* Page-locked host buffers: passing these to the *_batch calls skips the internal staging copy. */
+void* dra_host_alloc(size_t bytes);
+void  dra_host_free(void* p);
+
+/* Kernel launches issued by this context since creation (all of them this library's own kernels). */
+uint64_t dra_launch_count(const dra_ctx* ctx);
+/* When enabled, CUDA events bracket each kernel of the next calls; dra_get_timings returns the last
+ * call's per-stage device times in microseconds: [0] bucket-hist [1] bucket-scan [2] bucket-scatter
+ * [3] pack [4] all-gather.  Returns the number of floats written. */
+int  dra_set_profiling(dra_ctx* ctx, int enabled);
+int  dra_get_timings(dra_ctx* ctx, float* us, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRA_ALLOC_H */

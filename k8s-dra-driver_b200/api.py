@@ -1,0 +1,249 @@
+"""ctypes binding of libdra_alloc.so (include/dra_alloc.h) — the same entry points a Go driver binds
+with cgo.  This module is plumbing: every call below crosses the C ABI and runs the
+sm_100a kernels; nothing is computed in Python and nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import records as R
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libdra_alloc.so")
+
+OK, E_INVAL, E_CUDA, E_NCCL, E_NOMEM, E_STATE = 0, -1, -2, -3, -4, -5
+CFG_USE_GRAPH = 0x1
+F_NODE_SORTED, F_FRESH_INVENTORY = 0x1, 0x2
+
+
+class DraError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libdra_alloc: rc={code}: {msg}")
+        self.code = code
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p),
+                ("max_claims", C.c_uint32), ("flags", C.c_uint32)]
+
+
+# every symbol include/dra_alloc.h declares: name -> (restype, argtypes)
+_vp, _u32, _i32, _u64 = C.c_void_p, C.c_uint32, C.c_int, C.c_uint64
+SYMBOLS = {
+    "dra_abi_version": (_i32, []),
+    "dra_ctx_create": (_i32, [C.POINTER(_Cfg), C.POINTER(_vp)]),
+    "dra_ctx_destroy": (None, [_vp]),
+    "dra_last_error": (C.c_char_p, [_vp]),
+    "dra_set_placement_table": (_i32, [_vp, _u32, _vp]),
+    "dra_set_inventory": (_i32, [_vp, _vp, _u32, _vp, _u32]),
+    "dra_get_inventory": (_i32, [_vp, _vp, _u32]),
+    "dra_reset_inventory": (_i32, [_vp]),
+    "dra_allocate_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32]),
+    "dra_allocate_batch_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32]),
+    "dra_ctx_sync": (_i32, [_vp]),
+    "dra_unsuitable_batch": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _vp]),
+    "dra_deallocate_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32]),
+    "dra_comm_unique_id": (_i32, [_vp]),
+    "dra_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "dra_allocate_batch_gather_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _u32]),
+    "dra_host_alloc": (_vp, [C.c_size_t]),
+    "dra_host_free": (None, [_vp]),
+    "dra_launch_count": (_u64, [_vp]),
+    "dra_set_profiling": (_i32, [_vp, _i32]),
+    "dra_get_timings": (_i32, [_vp, _vp, _i32]),
+}
+
+_lib = None
+
+
+def load(build_if_stale: bool = True) -> C.CDLL:
+    """dlopen the in-tree library; raises if it is missing — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_stale:
+        from . import build as _b
+        try:
+            if _b.stale():
+                _b.build()
+        except RuntimeError:
+            if not os.path.exists(SO_PATH):
+                raise
+    if not os.path.exists(SO_PATH):
+        raise FileNotFoundError(f"{SO_PATH} not built: run `python __graft_entry__.py build`; "
+                                "the allocation path has no CPU fallback")
+    lib = C.CDLL(SO_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI and the header drift apart
+        fn.restype, fn.argtypes = res, args
+    if lib.dra_abi_version() != 1:
+        raise RuntimeError("libdra_alloc ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedBuffer:
+    """Page-locked host array from dra_host_alloc: passing it to Context calls skips staging."""
+
+    def __init__(self, n: int, dtype):
+        self._lib = load()
+        dtype = np.dtype(dtype)
+        self.nbytes = max(16, int(n) * dtype.itemsize)
+        self.ptr = self._lib.dra_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("dra_host_alloc failed")
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.dra_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One dra_ctx: one CUDA device, one stream, one inventory."""
+
+    def __init__(self, device: int = 0, stream: int | None = None, max_claims: int = 0, flags: int = 0):
+        self._lib = load()
+        cfg = _Cfg(1, device, C.c_void_p(stream) if stream else None, max_claims, flags)
+        h = C.c_void_p()
+        rc = self._lib.dra_ctx_create(C.byref(cfg), C.byref(h))
+        if rc != OK:
+            raise DraError(rc, (self._lib.dra_last_error(None) or b"").decode())
+        self._h = h
+        self.n_gpu = 0
+        self.n_node = 0
+
+    # -- plumbing -----------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != OK:
+            raise DraError(rc, (self._lib.dra_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dra_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state ----------------------------------------------------------------------------------------
+    def set_table(self, table: np.ndarray):
+        """table: PROF_DTYPE[MAX_MODELS, MAX_PROFILES]"""
+        t = np.ascontiguousarray(table, dtype=R.PROF_DTYPE)
+        assert t.shape == (R.MAX_MODELS, R.MAX_PROFILES)
+        for m in range(R.MAX_MODELS):
+            self._check(self._lib.dra_set_placement_table(self._h, m, _ptr(t[m])))
+
+    def set_inventory(self, gpus: np.ndarray, node_off: np.ndarray):
+        g = np.ascontiguousarray(gpus, dtype=R.GPU_DTYPE)
+        off = np.ascontiguousarray(node_off, dtype=np.uint32)
+        self._check(self._lib.dra_set_inventory(self._h, _ptr(g), len(g), _ptr(off), len(off) - 1))
+        self.n_gpu, self.n_node = len(g), len(off) - 1
+
+    def get_inventory(self) -> np.ndarray:
+        g = np.zeros(self.n_gpu, dtype=R.GPU_DTYPE)
+        self._check(self._lib.dra_get_inventory(self._h, _ptr(g), self.n_gpu))
+        return g
+
+    def reset_inventory(self):
+        self._check(self._lib.dra_reset_inventory(self._h))
+
+    def sync(self):
+        self._check(self._lib.dra_ctx_sync(self._h))
+
+    # -- the path ---------------------------------------------------------------------------------------
+    def allocate(self, claims: np.ndarray, out_off: np.ndarray | None = None, n_out: int | None = None,
+                 flags: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        c = claims if (claims.dtype == R.CLAIM_DTYPE and claims.flags.c_contiguous) else \
+            np.ascontiguousarray(claims, dtype=R.CLAIM_DTYPE)
+        oo = None if out_off is None else np.ascontiguousarray(out_off, dtype=np.uint32)
+        if n_out is None:
+            n_out = len(c) if oo is None else int(R.claim_slots(c, self.n_node).sum())
+        if out is None:
+            out = np.zeros(n_out, dtype=R.OUT_DTYPE)
+        self._check(self._lib.dra_allocate_batch(self._h, _ptr(c), len(c), _ptr(oo), _ptr(out), n_out, flags))
+        return out
+
+    def allocate_device(self, d_claims: int, n_claim: int, d_out_off: int | None, d_out: int, n_out: int,
+                        flags: int = 0):
+        """Device pointers (ints); enqueues on the context's stream, no synchronisation."""
+        self._check(self._lib.dra_allocate_batch_device(self._h, _ptr(d_claims), n_claim, _ptr(d_out_off),
+                                                        _ptr(d_out), n_out, flags))
+
+    def allocate_gather_device(self, d_claims: int, n_claim: int, d_out_off: int | None, d_out_all: int,
+                               n_out: int, n_per_rank: int, flags: int = 0):
+        self._check(self._lib.dra_allocate_batch_gather_device(self._h, _ptr(d_claims), n_claim,
+                                                               _ptr(d_out_off), _ptr(d_out_all), n_out,
+                                                               n_per_rank, flags))
+
+    def unsuitable(self, claims, pod_off, cand_nodes, cand_off) -> np.ndarray:
+        c = np.ascontiguousarray(claims, dtype=R.CLAIM_DTYPE)
+        po = np.ascontiguousarray(pod_off, dtype=np.uint32)
+        cn = np.ascontiguousarray(cand_nodes, dtype=np.uint32)
+        co = np.ascontiguousarray(cand_off, dtype=np.uint32)
+        n_pair = int(co[-1])
+        bits = np.zeros((n_pair + 7) // 8 + 8, dtype=np.uint8)
+        self._check(self._lib.dra_unsuitable_batch(self._h, _ptr(c), len(c), _ptr(po), len(po) - 1,
+                                                   _ptr(cn), _ptr(co), _ptr(bits)))
+        return bits[: (n_pair + 7) // 8]
+
+    def deallocate(self, claims, out, out_off=None):
+        c = np.ascontiguousarray(claims, dtype=R.CLAIM_DTYPE)
+        o = np.ascontiguousarray(out, dtype=R.OUT_DTYPE)
+        oo = None if out_off is None else np.ascontiguousarray(out_off, dtype=np.uint32)
+        self._check(self._lib.dra_deallocate_batch(self._h, _ptr(c), len(c), _ptr(oo), _ptr(o), len(o)))
+
+    # -- multi-GPU ------------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = load().dra_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != OK:
+            raise DraError(rc, (load().dra_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._check(self._lib.dra_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
+    # -- instrumentation ------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._lib.dra_launch_count(self._h))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.dra_set_profiling(self._h, 1 if on else 0))
+
+    def timings_us(self) -> dict:
+        buf = (C.c_float * 5)()
+        n = self._lib.dra_get_timings(self._h, C.cast(buf, C.c_void_p), 5)
+        names = ["bucket_hist", "bucket_scan", "bucket_scatter", "pack", "all_gather"]
+        return {names[i]: float(buf[i]) for i in range(n)}

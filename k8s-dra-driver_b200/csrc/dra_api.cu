@@ -1,0 +1,628 @@
+// dra_api.cu — C ABI of libdra_alloc.so (include/dra_alloc.h): context, staging, kernel chain, NCCL.
+//
+// No CPU fallback lives here: every entry point that computes anything launches the sm_100a kernels of
+// dra_device.cuh, and dra_ctx_create fails when there is no usable device.
+#include "dra_device.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace dra;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+// registry of dra_host_alloc buffers: passing one of these skips the staging copy
+std::mutex g_pin_mu;
+std::map<uintptr_t, size_t> g_pinned;
+
+bool is_pinned(const void* p, size_t bytes) {
+    if (!p) return false;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pinned.upper_bound((uintptr_t)p);
+    if (it == g_pinned.begin()) return false;
+    --it;
+    return (uintptr_t)p + bytes <= it->first + it->second;
+}
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        // libnccl.so.2 already mapped by the host runtime (torch) is reused by soname
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { err = std::string("dlopen libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy) { err = "libnccl: missing symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+}  // namespace
+
+struct dra_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint32_t cfg_flags = 0;
+
+    // inventory
+    uint32_t n_gpu = 0, n_node = 0;
+    uint4* d_inv_live = nullptr;
+    uint4* d_inv_pristine = nullptr;
+    uint32_t* d_node_off = nullptr;
+    uint32_t* d_tbl = nullptr;
+    dra_profile_tbl h_tbl[DRA_MAX_MODELS];
+    bool tbl_dirty = true;
+
+    // batch buffers (device)
+    size_t cap_claims = 0, cap_out = 0, cap_hist = 0, cap_nodes = 0, cap_pairs = 0, cap_pods = 0;
+    uint4* d_claims = nullptr;
+    uint4* d_sorted = nullptr;
+    uint32_t* d_out_off = nullptr;
+    uint2* d_out = nullptr;
+    uint16_t* d_rank = nullptr;
+    uint32_t* d_hist = nullptr;
+    uint32_t* d_claim_off = nullptr;
+    uint32_t *d_pod_off = nullptr, *d_cand_off = nullptr, *d_cand_nodes = nullptr, *d_pair_pod = nullptr, *d_bits = nullptr;
+
+    // error flags
+    uint32_t* d_err = nullptr;            // device memory
+    volatile uint32_t* h_err = nullptr;   // mapped pinned host memory
+    uint32_t* h_err_dev = nullptr;        // device alias of h_err
+
+    // pinned staging
+    uint8_t* h_in = nullptr;  size_t h_in_cap = 0;
+    uint8_t* h_out = nullptr; size_t h_out_cap = 0;
+
+    uint64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[8] = {};
+    bool ev_ok = false;
+    float timings[5] = {0, 0, 0, 0, 0};
+    int hist_smem_set = 0;
+
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+
+    std::string err;
+};
+
+namespace {
+
+int fail(dra_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do { cudaError_t e_ = (call);                                                                     \
+         if (e_ != cudaSuccess) return fail(ctx, DRA_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+template <class T>
+int grow(dra_ctx* ctx, T*& p, size_t& cap, size_t need, size_t slack = 16) {
+    if (need <= cap && p) return DRA_OK;
+    size_t ncap = std::max(need, cap + cap / 2) + slack;
+    if (p) CU(cudaFree(p));
+    p = nullptr;
+    CU(cudaMalloc((void**)&p, ncap * sizeof(T)));
+    cap = ncap;
+    return DRA_OK;
+}
+
+template <class T>
+int grow_nc(dra_ctx* ctx, T*& p, size_t have_cap, size_t new_cap) {   // companion buffer, cap tracked elsewhere
+    if (p && new_cap <= have_cap) return DRA_OK;
+    if (p) CU(cudaFree(p));
+    p = nullptr;
+    CU(cudaMalloc((void**)&p, new_cap * sizeof(T)));
+    return DRA_OK;
+}
+
+int grow_pinned(dra_ctx* ctx, uint8_t*& p, size_t& cap, size_t need) {
+    if (need <= cap && p) return DRA_OK;
+    size_t ncap = std::max(need, cap + cap / 2) + 256;
+    if (p) CU(cudaFreeHost(p));
+    p = nullptr;
+    CU(cudaHostAlloc((void**)&p, ncap, cudaHostAllocDefault));
+    cap = ncap;
+    return DRA_OK;
+}
+
+struct Tiling { uint32_t T, n_tiles; };
+Tiling tiling(uint32_t n_claim) {
+    uint32_t T = (n_claim + 63) / 64;
+    T = (T + 31) & ~31u;
+    T = std::max(256u, std::min(T, 65504u));
+    uint32_t n_tiles = n_claim ? (n_claim + T - 1) / T : 1;
+    return {T, n_tiles};
+}
+
+int ensure_batch(dra_ctx* ctx, uint32_t n_claim, uint32_t n_out, bool own_io) {
+    size_t need_c = std::max<size_t>(n_claim, 1), need_o = std::max<size_t>(n_out, 1);
+    if (need_c > ctx->cap_claims || !ctx->d_sorted) {
+        size_t ncap = std::max(need_c, ctx->cap_claims + ctx->cap_claims / 2) + 64;
+        int rc;
+        if ((rc = grow_nc(ctx, ctx->d_claims, 0, ncap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_sorted, 0, ncap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_out_off, 0, ncap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_rank, 0, ncap))) return rc;
+        ctx->cap_claims = ncap;
+    }
+    if (own_io) { int rc = grow(ctx, ctx->d_out, ctx->cap_out, need_o, 64); if (rc) return rc; }
+    Tiling t = tiling(n_claim);
+    size_t need_h = (size_t)t.n_tiles * (ctx->n_node + 1);
+    int rc = grow(ctx, ctx->d_hist, ctx->cap_hist, need_h, 64);
+    return rc;
+}
+
+Err err_of(dra_ctx* ctx) { return Err{ctx->d_err, (volatile uint32_t*)ctx->h_err_dev}; }
+
+int upload_table(dra_ctx* ctx) {
+    if (!ctx->tbl_dirty) return DRA_OK;
+    CU(cudaMemcpyAsync(ctx->d_tbl, ctx->h_tbl, sizeof ctx->h_tbl, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // h_tbl is pageable; keep it simple (rare call)
+    ctx->tbl_dirty = false;
+    return DRA_OK;
+}
+
+struct Prof {
+    dra_ctx* c; int i = 0;
+    explicit Prof(dra_ctx* ctx) : c(ctx) { if (c->profiling) cudaEventRecord(c->ev[0], c->stream); }
+    void mark() { if (c->profiling) cudaEventRecord(c->ev[++i], c->stream); }
+};
+
+// The kernel chain of one Allocate batch on device-resident inputs.  Enqueues only.
+int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
+                    uint2* d_out, uint32_t n_out, uint32_t flags) {
+    if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
+    int rc = upload_table(ctx);
+    if (rc) return rc;
+    const uint32_t n_node = ctx->n_node;
+    Err err = err_of(ctx);
+    Prof prof(ctx);
+
+    if (flags & DRA_F_NODE_SORTED) {
+        uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
+        k_sorted_prep<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
+                                                       ctx->d_sorted, d_out, n_out, err);
+        ctx->launches += 1;
+        prof.mark(); prof.mark(); prof.mark();
+    } else {
+        Tiling t = tiling(n_claim);
+        size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
+        if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
+        if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
+            CU(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->hist_smem_set = (int)smem;
+        }
+        k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
+        prof.mark();
+        k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off);
+        prof.mark();
+        uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
+        k_bucket_scatter<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
+                                                          ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err);
+        prof.mark();
+        ctx->launches += 3;
+    }
+
+    PackArgs a;
+    a.sorted = ctx->d_sorted;
+    a.claim_off = ctx->d_claim_off;
+    a.inv_src = (flags & DRA_F_FRESH_INVENTORY) ? ctx->d_inv_pristine : ctx->d_inv_live;
+    a.inv_dst = ctx->d_inv_live;
+    a.node_off = ctx->d_node_off;
+    a.tbl = ctx->d_tbl;
+    a.out = d_out; a.n_out = n_out; a.n_node = n_node; a.have_off = d_out_off != nullptr;
+    a.err = err;
+    if (n_node) {
+        if (n_node <= 148u * 16u) k_pack<1><<<n_node, 32, 0, ctx->stream>>>(a);
+        else k_pack<4><<<std::min((n_node + 3) / 4, 148u * 8u), 128, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
+    }
+    prof.mark();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return DRA_OK;
+}
+
+int collect_timings(dra_ctx* ctx, int n_marks) {
+    if (!ctx->profiling) return DRA_OK;
+    for (int i = 0; i < 5; ++i) ctx->timings[i] = 0.f;
+    for (int i = 0; i < n_marks && i < 5; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->timings[i] = ms * 1000.f;
+    }
+    (void)cudaGetLastError();   // an event that was never recorded is not an error of the batch
+    return DRA_OK;
+}
+
+int check_err(dra_ctx* ctx) {
+    uint32_t oor = ctx->h_err[ERR_OUT_RANGE], ns = ctx->h_err[ERR_NOT_SORTED];
+    if (!oor && !ns) return DRA_OK;
+    for (uint32_t i = 0; i < ERR_WORDS; ++i) ctx->h_err[i] = 0;
+    cudaMemsetAsync(ctx->d_err, 0, ERR_WORDS * sizeof(uint32_t), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (ns) return fail(ctx, DRA_E_INVAL, "DRA_F_NODE_SORTED given but claims are not sorted by node; inventory unchanged");
+    return fail(ctx, DRA_E_INVAL, "out_off/n_out: a claim's slots fall outside out[]; inventory state is undefined, reset it");
+}
+
+}  // namespace
+
+extern "C" {
+
+int dra_abi_version(void) { return (int)DRA_ABI_VERSION; }
+
+const char* dra_last_error(const dra_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int dra_ctx_create(const dra_cfg* cfg, dra_ctx** out) {
+    dra_ctx* ctx = nullptr;   // for CU(): errors go to the thread-local create error
+    if (!cfg || !out) return fail(nullptr, DRA_E_INVAL, "null argument");
+    if (cfg->abi_version != DRA_ABI_VERSION) return fail(nullptr, DRA_E_INVAL, "abi_version %u != %u", cfg->abi_version, DRA_ABI_VERSION);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DRA_E_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, DRA_E_INVAL, "device %d out of range", cfg->device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(nullptr, DRA_E_CUDA, "device %d is sm_%d%d; this build is sm_100a only", cfg->device, prop.major, prop.minor);
+    CU(cudaSetDevice(cfg->device));
+    dra_ctx* c = new dra_ctx();
+    c->device = cfg->device;
+    c->cfg_flags = cfg->flags;
+    ctx = c;
+    auto bail = [&](int rc) { g_create_err = c->err; dra_ctx_destroy(c); return rc; };
+    if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(c, DRA_E_CUDA, "cudaStreamCreate"));
+        c->own_stream = true;
+    }
+    memset(c->h_tbl, 0, sizeof c->h_tbl);
+    if (cudaMalloc((void**)&c->d_tbl, sizeof c->h_tbl) != cudaSuccess) return bail(fail(c, DRA_E_NOMEM, "cudaMalloc table"));
+    if (cudaMalloc((void**)&c->d_err, ERR_WORDS * sizeof(uint32_t)) != cudaSuccess) return bail(fail(c, DRA_E_NOMEM, "cudaMalloc err"));
+    cudaMemset(c->d_err, 0, ERR_WORDS * sizeof(uint32_t));
+    void* he = nullptr;
+    if (cudaHostAlloc(&he, ERR_WORDS * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) return bail(fail(c, DRA_E_NOMEM, "cudaHostAlloc err"));
+    c->h_err = (volatile uint32_t*)he;
+    for (uint32_t i = 0; i < ERR_WORDS; ++i) c->h_err[i] = 0;
+    if (cudaHostGetDevicePointer((void**)&c->h_err_dev, he, 0) != cudaSuccess) return bail(fail(c, DRA_E_CUDA, "cudaHostGetDevicePointer"));
+    for (int i = 0; i < 8; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(fail(c, DRA_E_CUDA, "cudaEventCreate"));
+    c->ev_ok = true;
+    if (cfg->max_claims) { int rc = ensure_batch(c, cfg->max_claims, cfg->max_claims, true); if (rc) return bail(rc); }
+    *out = c;
+    return DRA_OK;
+}
+
+void dra_ctx_destroy(dra_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) { std::lock_guard<std::mutex> lk(g_nccl_mu); if (g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm); }
+    void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
+                   c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
+                   c->d_pair_pod, c->d_bits, c->d_err};
+    for (void* p : dev) if (p) cudaFree(p);
+    if (c->h_err) cudaFreeHost((void*)c->h_err);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int dra_set_placement_table(dra_ctx* ctx, uint32_t model, const dra_profile_tbl* tbl) {
+    if (!ctx || !tbl) return DRA_E_INVAL;
+    if (model >= DRA_MAX_MODELS) return fail(ctx, DRA_E_INVAL, "model %u >= %u", model, DRA_MAX_MODELS);
+    for (uint32_t p = 0; p < DRA_MAX_PROFILES; ++p) {
+        const dra_prof_ent& e = tbl->ent[p];
+        if (!e.start_mask) continue;
+        if (e.size < 1 || e.size > 16) return fail(ctx, DRA_E_INVAL, "profile %u: size %u", p, e.size);
+        int hi = 15; while (!((e.start_mask >> hi) & 1)) --hi;
+        if (hi + e.size > 16) return fail(ctx, DRA_E_INVAL, "profile %u: start %d + size %u > 16", p, hi, e.size);
+    }
+    ctx->h_tbl[model] = *tbl;
+    ctx->tbl_dirty = true;
+    return DRA_OK;
+}
+
+int dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node) {
+    if (!ctx || !node_off || (n_gpu && !gpus)) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (node_off[0] != 0 || node_off[n_node] != n_gpu) return fail(ctx, DRA_E_INVAL, "node_off must span [0, n_gpu]");
+    for (uint32_t n = 0; n < n_node; ++n) {
+        if (node_off[n + 1] < node_off[n]) return fail(ctx, DRA_E_INVAL, "node_off not monotone at node %u", n);
+        if (node_off[n + 1] - node_off[n] > DRA_MAX_GPUS_PER_NODE) return fail(ctx, DRA_E_INVAL, "node %u has more than %u GPUs", n, DRA_MAX_GPUS_PER_NODE);
+        for (uint32_t g = node_off[n]; g < node_off[n + 1]; ++g) {
+            if (gpus[g].model >= DRA_MAX_MODELS) return fail(ctx, DRA_E_INVAL, "gpu %u: model %u", g, gpus[g].model);
+            if (gpus[g].node != n) return fail(ctx, DRA_E_INVAL, "gpu %u: node field %u, expected %u", g, gpus[g].node, n);
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_gpu + 8 > ctx->cap_nodes || !ctx->d_inv_live) {   // cap_nodes doubles as "inventory capacity"
+        if (ctx->d_inv_live) CU(cudaFree(ctx->d_inv_live));
+        if (ctx->d_inv_pristine) CU(cudaFree(ctx->d_inv_pristine));
+        ctx->d_inv_live = ctx->d_inv_pristine = nullptr;
+        size_t cap = (size_t)n_gpu + 64;
+        CU(cudaMalloc((void**)&ctx->d_inv_live, cap * 16));
+        CU(cudaMalloc((void**)&ctx->d_inv_pristine, cap * 16));
+        ctx->cap_nodes = cap;
+    }
+    if (ctx->d_node_off) CU(cudaFree(ctx->d_node_off));
+    if (ctx->d_claim_off) CU(cudaFree(ctx->d_claim_off));
+    ctx->d_node_off = ctx->d_claim_off = nullptr;
+    CU(cudaMalloc((void**)&ctx->d_node_off, ((size_t)n_node + 8) * 4));
+    CU(cudaMalloc((void**)&ctx->d_claim_off, ((size_t)n_node + 8) * 4));
+    if (n_gpu) CU(cudaMemcpy(ctx->d_inv_pristine, gpus, (size_t)n_gpu * 16, cudaMemcpyHostToDevice));
+    if (n_gpu) CU(cudaMemcpy(ctx->d_inv_live, gpus, (size_t)n_gpu * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_node_off, node_off, ((size_t)n_node + 1) * 4, cudaMemcpyHostToDevice));
+    ctx->n_gpu = n_gpu; ctx->n_node = n_node;
+    ctx->cap_hist = 0;  // histogram geometry depends on n_node
+    if (ctx->d_hist) { CU(cudaFree(ctx->d_hist)); ctx->d_hist = nullptr; }
+    return DRA_OK;
+}
+
+int dra_get_inventory(dra_ctx* ctx, dra_gpu_rec* gpus, uint32_t n_gpu) {
+    if (!ctx || !gpus) return DRA_E_INVAL;
+    if (n_gpu != ctx->n_gpu) return fail(ctx, DRA_E_INVAL, "n_gpu %u != inventory size %u", n_gpu, ctx->n_gpu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_gpu) CU(cudaMemcpy(gpus, ctx->d_inv_live, (size_t)n_gpu * 16, cudaMemcpyDeviceToHost));
+    return DRA_OK;
+}
+
+int dra_reset_inventory(dra_ctx* ctx) {
+    if (!ctx) return DRA_E_INVAL;
+    if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "no inventory");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->n_gpu) CU(cudaMemcpyAsync(ctx->d_inv_live, ctx->d_inv_pristine, (size_t)ctx->n_gpu * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DRA_OK;
+}
+
+int dra_ctx_sync(dra_ctx* ctx) {
+    if (!ctx) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    collect_timings(ctx, 5);
+    return check_err(ctx);
+}
+
+int dra_allocate_batch_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
+                              dra_out_rec* d_out, uint32_t n_out, uint32_t flags) {
+    if (!ctx || (n_claim && (!d_claims || !d_out))) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_batch(ctx, n_claim, n_out, false);
+    if (rc) return rc;
+    return launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)d_out, n_out, flags);
+}
+
+int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* out_off,
+                       dra_out_rec* out, uint32_t n_out, uint32_t flags) {
+    if (!ctx || (n_claim && (!claims || !out))) return DRA_E_INVAL;
+    if (!out_off && n_out < n_claim) return fail(ctx, DRA_E_INVAL, "n_out %u < n_claim %u without out_off", n_out, n_claim);
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_batch(ctx, n_claim, n_out, true);
+    if (rc) return rc;
+    const size_t cb = (size_t)n_claim * 16, ob = out_off ? (size_t)n_claim * 4 : 0, rb = (size_t)n_out * 8;
+    // host -> device (staged through pinned memory unless the caller's buffers are dra_host_alloc'ed)
+    const void* src_c = claims; const void* src_o = out_off;
+    if (cb && !is_pinned(claims, cb)) {
+        if ((rc = grow_pinned(ctx, ctx->h_in, ctx->h_in_cap, cb + ob))) return rc;
+        memcpy(ctx->h_in, claims, cb); src_c = ctx->h_in;
+        if (ob) { memcpy(ctx->h_in + cb, out_off, ob); src_o = ctx->h_in + cb; }
+    } else if (ob && !is_pinned(out_off, ob)) {
+        if ((rc = grow_pinned(ctx, ctx->h_in, ctx->h_in_cap, ob))) return rc;
+        memcpy(ctx->h_in, out_off, ob); src_o = ctx->h_in;
+    }
+    if (cb) CU(cudaMemcpyAsync(ctx->d_claims, src_c, cb, cudaMemcpyHostToDevice, ctx->stream));
+    if (ob) CU(cudaMemcpyAsync(ctx->d_out_off, src_o, ob, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_allocate(ctx, ctx->d_claims, n_claim, out_off ? ctx->d_out_off : nullptr, ctx->d_out, n_out, flags);
+    if (rc) return rc;
+    const bool direct = rb && is_pinned(out, rb);
+    if (rb && !direct && (rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, rb))) return rc;
+    if (rb) CU(cudaMemcpyAsync(direct ? (void*)out : (void*)ctx->h_out, ctx->d_out, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    collect_timings(ctx, 4);
+    if ((rc = check_err(ctx))) return rc;
+    if (rb && !direct) memcpy(out, ctx->h_out, rb);
+    return DRA_OK;
+}
+
+int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* pod_off, uint32_t n_pod,
+                         const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits) {
+    if (!ctx || !pod_off || !cand_off || (n_claim && !claims)) return DRA_E_INVAL;
+    if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
+    if (pod_off[n_pod] != n_claim) return fail(ctx, DRA_E_INVAL, "pod_off[n_pod] != n_claim");
+    const uint32_t n_pair = cand_off[n_pod];
+    if (n_pair && (!cand_nodes || !suitable_bits)) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_batch(ctx, n_claim, 1, true);
+    if (rc) return rc;
+    if ((rc = upload_table(ctx))) return rc;
+    if (n_pod + 8 > ctx->cap_pods) {
+        size_t cap = (size_t)n_pod + n_pod / 2 + 64;
+        if ((rc = grow_nc(ctx, ctx->d_pod_off, 0, cap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_cand_off, 0, cap))) return rc;
+        ctx->cap_pods = cap;
+    }
+    if (n_pair + 64 > ctx->cap_pairs) {
+        size_t cap = (size_t)n_pair + n_pair / 2 + 128;
+        if ((rc = grow_nc(ctx, ctx->d_cand_nodes, 0, cap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_pair_pod, 0, cap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_bits, 0, cap / 32 + 8))) return rc;
+        ctx->cap_pairs = cap;
+    }
+    const size_t words = ((size_t)n_pair + 31) / 32;
+    // pair -> pod expansion on the host side of the staging buffer (O(n_pair) integer fill)
+    const size_t stage = (size_t)n_claim * 16 + ((size_t)n_pod + 1) * 8 + (size_t)n_pair * 8 + words * 4 + 64;
+    if ((rc = grow_pinned(ctx, ctx->h_in, ctx->h_in_cap, stage))) return rc;
+    uint8_t* p = ctx->h_in;
+    memcpy(p, claims, (size_t)n_claim * 16); uint8_t* h_claims = p; p += (size_t)n_claim * 16;
+    memcpy(p, pod_off, ((size_t)n_pod + 1) * 4); uint8_t* h_pod = p; p += ((size_t)n_pod + 1) * 4;
+    memcpy(p, cand_off, ((size_t)n_pod + 1) * 4); uint8_t* h_coff = p; p += ((size_t)n_pod + 1) * 4;
+    if (n_pair) memcpy(p, cand_nodes, (size_t)n_pair * 4);
+    uint8_t* h_cn = p; p += (size_t)n_pair * 4;
+    uint32_t* h_pp = (uint32_t*)p;
+    for (uint32_t q = 0; q < n_pod; ++q) {
+        if (cand_off[q + 1] < cand_off[q] || cand_off[q + 1] > n_pair) return fail(ctx, DRA_E_INVAL, "cand_off not monotone at pod %u", q);
+        if (pod_off[q + 1] < pod_off[q]) return fail(ctx, DRA_E_INVAL, "pod_off not monotone at pod %u", q);
+        for (uint32_t k = cand_off[q]; k < cand_off[q + 1]; ++k) h_pp[k] = q;
+    }
+    if (n_claim) CU(cudaMemcpyAsync(ctx->d_claims, h_claims, (size_t)n_claim * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pod_off, h_pod, ((size_t)n_pod + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_cand_off, h_coff, ((size_t)n_pod + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_pair) {
+        CU(cudaMemcpyAsync(ctx->d_cand_nodes, h_cn, (size_t)n_pair * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_pair_pod, h_pp, (size_t)n_pair * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_bits, 0, words * 4, ctx->stream));
+        UnsArgs a;
+        a.claims = ctx->d_claims; a.pod_off = ctx->d_pod_off; a.n_pod = n_pod;
+        a.cand_nodes = ctx->d_cand_nodes; a.cand_off = ctx->d_cand_off; a.pair_pod = ctx->d_pair_pod; a.n_pair = n_pair;
+        a.inv = ctx->d_inv_live; a.node_off = ctx->d_node_off; a.n_node = ctx->n_node; a.tbl = ctx->d_tbl; a.bits = ctx->d_bits;
+        Prof prof(ctx);
+        uint32_t grid = std::min((n_pair + 7) / 8, 148u * 8u);
+        k_unsuitable<8><<<grid, 256, 0, ctx->stream>>>(a);
+        prof.mark();
+        ctx->launches += 1;
+        if ((rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, words * 4))) return rc;
+        CU(cudaMemcpyAsync(ctx->h_out, ctx->d_bits, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "k_unsuitable: %s", cudaGetErrorString(e));
+    collect_timings(ctx, 1);
+    if (n_pair) memcpy(suitable_bits, ctx->h_out, ((size_t)n_pair + 7) / 8);
+    return DRA_OK;
+}
+
+int dra_deallocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* out_off,
+                         const dra_out_rec* out, uint32_t n_out) {
+    if (!ctx || (n_claim && (!claims || !out))) return DRA_E_INVAL;
+    if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
+    if (!n_claim) return DRA_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_batch(ctx, n_claim, n_out, true);
+    if (rc) return rc;
+    const size_t cb = (size_t)n_claim * 16, ob = out_off ? (size_t)n_claim * 4 : 0, rb = (size_t)n_out * 8;
+    if ((rc = grow_pinned(ctx, ctx->h_in, ctx->h_in_cap, cb + ob + rb))) return rc;
+    memcpy(ctx->h_in, claims, cb);
+    if (ob) memcpy(ctx->h_in + cb, out_off, ob);
+    memcpy(ctx->h_in + cb + ob, out, rb);
+    CU(cudaMemcpyAsync(ctx->d_claims, ctx->h_in, cb, cudaMemcpyHostToDevice, ctx->stream));
+    if (ob) CU(cudaMemcpyAsync(ctx->d_out_off, ctx->h_in + cb, ob, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_out, ctx->h_in + cb + ob, rb, cudaMemcpyHostToDevice, ctx->stream));
+    k_dealloc<<<(n_claim + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_claims, n_claim, out_off ? ctx->d_out_off : nullptr,
+                                                             ctx->d_out, n_out, (uint32_t*)ctx->d_inv_live, ctx->n_gpu, err_of(ctx));
+    ctx->launches += 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "k_dealloc: %s", cudaGetErrorString(e));
+    return check_err(ctx);
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------
+
+int dra_comm_unique_id(void* id128) {
+    if (!id128) return DRA_E_INVAL;
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_err = err; return DRA_E_NCCL; }
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_err = "ncclGetUniqueId failed"; return DRA_E_NCCL; }
+    memcpy(id128, &id, 128);
+    return DRA_OK;
+}
+
+int dra_comm_init(dra_ctx* ctx, const void* id128, int rank, int world) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    {
+        std::lock_guard<std::mutex> lk(g_nccl_mu);
+        std::string err;
+        if (!g_nccl.load(err)) return fail(ctx, DRA_E_NCCL, "%s", err.c_str());
+    }
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+    if (r != ncclSuccess) return fail(ctx, DRA_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    ctx->rank = rank; ctx->world = world;
+    return DRA_OK;
+}
+
+int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
+                                     dra_out_rec* d_out_all, uint32_t n_out, uint32_t n_per_rank, uint32_t flags) {
+    if (!ctx || !d_out_all || (n_claim && !d_claims)) return DRA_E_INVAL;
+    if (!ctx->comm) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called");
+    if (n_out > n_per_rank) return fail(ctx, DRA_E_INVAL, "n_out %u > n_per_rank %u", n_out, n_per_rank);
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_batch(ctx, n_claim, n_out, false);
+    if (rc) return rc;
+    dra_out_rec* mine = d_out_all + (size_t)ctx->rank * n_per_rank;
+    if (n_per_rank > n_out) CU(cudaMemsetAsync(mine + n_out, 0, (size_t)(n_per_rank - n_out) * 8, ctx->stream));
+    rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags);
+    if (rc) return rc;
+    // the one collective of the path: every rank's OutRec slice to every rank (in place), same stream
+    ncclResult_t r = g_nccl.AllGather(mine, d_out_all, (size_t)n_per_rank * 8, ncclUint8, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) return fail(ctx, DRA_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    if (ctx->profiling) cudaEventRecord(ctx->ev[5], ctx->stream);
+    return DRA_OK;
+}
+
+// ---- host memory + instrumentation -----------------------------------------------------------------
+
+void* dra_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pinned[(uintptr_t)p] = bytes ? bytes : 16;
+    return p;
+}
+
+void dra_host_free(void* p) {
+    if (!p) return;
+    { std::lock_guard<std::mutex> lk(g_pin_mu); g_pinned.erase((uintptr_t)p); }
+    cudaFreeHost(p);
+}
+
+uint64_t dra_launch_count(const dra_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dra_set_profiling(dra_ctx* ctx, int enabled) {
+    if (!ctx) return DRA_E_INVAL;
+    ctx->profiling = enabled != 0;
+    return DRA_OK;
+}
+
+int dra_get_timings(dra_ctx* ctx, float* us, int n) {
+    if (!ctx || !us) return 0;
+    int m = std::min(n, 5);
+    for (int i = 0; i < m; ++i) us[i] = ctx->timings[i];
+    return m;
+}
+
+}  // extern "C"

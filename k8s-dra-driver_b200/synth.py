@@ -1,0 +1,217 @@
+"""Seeded synthetic workloads for the five BASELINE.json configs.
+
+SplitMix64, base seed 0x0D5A110C, per-config seed = base + config number.  The same buffers feed the CPU
+oracle and the CUDA path; nothing here reads /root/reference.  The reference ships no workloads of its
+own for this path — the only in-tree workload shapes are the quickstart specs
+(demo/specs/quickstart/gpu-test4.yaml:19-44 etc.), reproduced in tests/ as fixtures.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import records as R
+
+BASE_SEED = 0x0D5A110C
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+
+
+def splitmix64(seed: int, n: int) -> np.ndarray:
+    """n outputs of SplitMix64 started at `seed` (vectorised: state_i = seed + (i+1)*golden)."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + _GOLDEN * np.arange(1, n + 1, dtype=np.uint64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+@dataclass
+class Workload:
+    name: str
+    gpus: np.ndarray          # GPU_DTYPE[n_gpu]
+    node_off: np.ndarray      # uint32[n_node+1]
+    table: np.ndarray         # PROF_DTYPE[16,16]
+    claims: np.ndarray        # CLAIM_DTYPE[n_claim], generation (unsorted) order
+    out_off: np.ndarray | None = None
+    n_out: int = 0
+
+    @property
+    def n_node(self) -> int:
+        return len(self.node_off) - 1
+
+    @property
+    def n_gpu(self) -> int:
+        return len(self.gpus)
+
+    @property
+    def n_claim(self) -> int:
+        return len(self.claims)
+
+    def node_sorted(self) -> "Workload":
+        """Stable sort of the claims by node (the input order SURVEY §8d quotes for cfg2)."""
+        order = np.argsort(self.claims["node"], kind="stable")
+        w = Workload(self.name + "+sorted", self.gpus.copy(), self.node_off, self.table,
+                     self.claims[order].copy())
+        w.finish()
+        return w
+
+    def finish(self) -> "Workload":
+        if not np.any((self.claims["kind"] == R.KIND_GPU) & (self.claims["count"] != 1)):
+            self.out_off, self.n_out = None, self.n_claim
+        else:
+            self.out_off, self.n_out = R.out_offsets(self.claims, self.n_node)
+        return self
+
+    def algorithmic_bytes(self) -> int:
+        """16 B/claim read + 16 B/GPU read + 8 B/slot written."""
+        return 16 * self.n_claim + 16 * self.n_gpu + 8 * self.n_out
+
+
+def _mig_mix(n_claim: int, n_node: int, seed: int, node_base: int = 0) -> np.ndarray:
+    r = splitmix64(seed, 2 * n_claim)
+    pick = (r[0::2] % np.uint64(100)).astype(np.int64)
+    prof = np.where(pick < 40, R.GI_1_SLICE,
+                    np.where(pick < 70, R.GI_2_SLICE, np.where(pick < 90, R.GI_3_SLICE, R.GI_7_SLICE)))
+    c = np.zeros(n_claim, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_MIG
+    c["profile"] = prof
+    c["count"] = 1
+    c["node"] = (r[1::2] % np.uint64(n_node)).astype(np.uint32) + np.uint32(node_base)
+    return c
+
+
+def cfg1() -> Workload:
+    """64 full-GPU claims over one 8-GPU node: first 8 succeed (gpu 0..7), 56 fail."""
+    g, off = R.make_inventory([8], mig=False)
+    c = np.zeros(64, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_GPU
+    c["count"] = 1
+    return Workload("cfg1", g, off, R.default_table(), c).finish()
+
+
+def cfg2(n_claim: int = 10_000, n_node: int = 125, gpus_per_node: int = 8, seed_off: int = 2) -> Workload:
+    """10k mixed 1g/2g/3g/7g MIG claims (40/30/20/10 %) over 125 nodes x 8 empty MIG-enabled GPUs."""
+    g, off = R.make_inventory([gpus_per_node] * n_node, mig=True)
+    c = _mig_mix(n_claim, n_node, BASE_SEED + seed_off)
+    return Workload("cfg2", g, off, R.default_table(), c).finish()
+
+
+def cfg3(n_claim: int = 100_000, n_node: int = 1000) -> Workload:
+    """100k claims x 8k GPUs, same mix; nodes are sharded contiguously over ranks."""
+    w = cfg2(n_claim, n_node, 8, seed_off=3)
+    w.name = "cfg3"
+    return w
+
+
+def cfg3_shard(rank: int, world: int, claims_per_rank: int = 12_500, nodes_per_rank: int = 125) -> Workload:
+    """Rank-local slice of a cfg3-shaped job (weak scaling: every rank owns nodes_per_rank nodes and
+    the claims_per_rank claims that select them).  Node indices are LOCAL to the rank's inventory."""
+    g, off = R.make_inventory([8] * nodes_per_rank, mig=True)
+    c = _mig_mix(claims_per_rank, nodes_per_rank, BASE_SEED + 3 + 1000 * (rank + 1))
+    return Workload(f"cfg3[{rank}/{world}]", g, off, R.default_table(), c).finish()
+
+
+def cfg4(n_claim: int = 10_000, n_node: int = 125) -> Workload:
+    """MPS / time-slice shared claims with a per-claim memory limit (spec §7, extension)."""
+    g, off = R.make_inventory([8] * n_node, mig=False, mem_free_mib=40960)
+    r = splitmix64(BASE_SEED + 4, 3 * n_claim)
+    mps = (r[0::3] & np.uint64(1)).astype(bool)
+    limits = np.array([1024, 2048, 4096, 8192, 10240], dtype=np.uint32)
+    c = np.zeros(n_claim, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_SHARED
+    c["count"] = 1
+    c["mem_limit_mib"] = np.where(mps, limits[(r[1::3] % np.uint64(5)).astype(np.int64)], 0)
+    c["node"] = (r[2::3] % np.uint64(n_node)).astype(np.uint32)
+    return Workload("cfg4", g, off, R.default_table(), c).finish()
+
+
+_FRAG = np.array([0x55, 0xAA, 0x33, 0xCC, 0x0F, 0xF0, 0x5A, 0xA5, 0x7E, 0x3C, 0x66, 0x99, 0x11, 0x88],
+                 dtype=np.uint16)
+
+
+def cfg5(n_claim: int = 50_000, n_node: int = 64) -> Workload:
+    """Adversarial fragmentation: 50k 1g claims into 512 pre-fragmented GPUs."""
+    g, off = R.make_inventory([8] * n_node, mig=True)
+    r = splitmix64(BASE_SEED + 5, len(g) + n_claim)
+    g["busy"] = _FRAG[(r[: len(g)] % np.uint64(len(_FRAG))).astype(np.int64)]
+    c = np.zeros(n_claim, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_MIG
+    c["profile"] = R.GI_1_SLICE
+    c["count"] = 1
+    c["node"] = (r[len(g):] % np.uint64(n_node)).astype(np.uint32)
+    return Workload("cfg5", g, off, R.default_table(), c).finish()
+
+
+def mixed(n_claim: int = 4000, n_node: int = 37, seed: int = 7, invalid: bool = True) -> Workload:
+    """Everything at once, for parity fuzzing: ragged heterogeneous nodes (0..32 GPUs, two models,
+    MIG and non-MIG, pre-occupied, unavailable), all three kinds, count > 1, co-location groups,
+    unsupported profiles and (optionally) malformed claims."""
+    r = splitmix64(BASE_SEED + 100 + seed, 8 * (n_node * 40 + n_claim) + 64)
+    pos = [0]
+
+    def take(n):
+        s = pos[0]
+        pos[0] += n
+        return r[s: s + n]
+
+    sizes = (take(n_node) % np.uint64(12)).astype(np.int64)
+    sizes[sizes == 11] = 32          # a few full-width nodes
+    sizes[:: max(1, n_node // 5)] = 0  # and some empty ones
+    if n_node > 2:
+        sizes[1] = 8
+    g, off = R.make_inventory(list(sizes), mig=True)
+    ng = len(g)
+    a = take(max(ng, 1) * 4)
+    g["flags"] = np.where(a[0:ng] % np.uint64(3) == 0, 0, R.GPU_MIG_ENABLED).astype(np.uint8)
+    g["flags"] |= np.where(a[ng:2 * ng] % np.uint64(17) == 0, R.GPU_UNAVAILABLE, 0).astype(np.uint8)
+    g["model"] = (a[2 * ng:3 * ng] % np.uint64(4) == 0).astype(np.uint8)
+    pre = (a[3 * ng:4 * ng] % np.uint64(256)).astype(np.uint16)
+    pre = np.where(a[3 * ng:4 * ng] % np.uint64(5) < 2, pre, 0).astype(np.uint16)
+    g["busy"] = np.where(g["model"] == 1, pre & 0xF, pre)
+    g["busy"] = np.where(g["flags"] & R.GPU_MIG_ENABLED, g["busy"], 0)
+    g["mem_free_mib"] = 16384
+
+    b = take(n_claim * 6)
+    c = np.zeros(n_claim, dtype=R.CLAIM_DTYPE)
+    k = (b[0::6] % np.uint64(10)).astype(np.int64)
+    c["kind"] = np.where(k < 6, R.KIND_MIG, np.where(k < 8, R.KIND_GPU, R.KIND_SHARED))
+    profs = np.array([0, 0, 0, 1, 1, 2, 3, 4, 7, 9, 5, 6], dtype=np.uint8)
+    c["profile"] = profs[(b[1::6] % np.uint64(len(profs))).astype(np.int64)]
+    cnt = (b[2::6] % np.uint64(8)).astype(np.int64)
+    c["count"] = np.where(c["kind"] == R.KIND_GPU, np.where(cnt < 5, 1, cnt - 3), 1)
+    c["node"] = (b[3::6] % np.uint64(n_node)).astype(np.uint32)
+    c["mem_limit_mib"] = np.where(c["kind"] == R.KIND_SHARED,
+                                  (b[4::6] % np.uint64(5)).astype(np.uint32) * 3000, 0)
+    # co-location groups: runs of 2..5 consecutive MIG claims on one node share a group id
+    gsel = b[5::6]
+    i = 0
+    gid = 1
+    while i < n_claim:
+        if gsel[i] % np.uint64(9) == 0:
+            ln = int(gsel[i] >> np.uint64(8)) % 4 + 2
+            j = min(n_claim, i + ln)
+            c["kind"][i:j] = R.KIND_MIG
+            c["count"][i:j] = 1
+            c["mem_limit_mib"][i:j] = 0
+            c["node"][i:j] = c["node"][i]
+            c["group"][i:j] = gid
+            small = np.array([0, 0, 1, 0, 2], dtype=np.uint8)
+            c["profile"][i:j] = small[(gsel[i:j] >> np.uint64(16)).astype(np.int64) % 5]
+            gid += 1
+            i = j
+        else:
+            i += 1
+    if invalid:
+        bad = take(n_claim)
+        c["kind"] = np.where(bad % np.uint64(97) == 0, 3, c["kind"])
+        c["node"] = np.where(bad % np.uint64(89) == 1, n_node + 5, c["node"])
+        c["count"] = np.where((bad % np.uint64(83) == 2) & (c["kind"] == R.KIND_GPU), 0, c["count"])
+        c["count"] = np.where((bad % np.uint64(83) == 3) & (c["kind"] == R.KIND_GPU), 40, c["count"])
+        c["profile"] = np.where((bad % np.uint64(79) == 4) & (c["kind"] == R.KIND_MIG), 200, c["profile"])
+    w = Workload(f"mixed{seed}", g, off, R.default_table(), c)
+    w.out_off, w.n_out = R.out_offsets(c, n_node)
+    return w
+
+
+CONFIGS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}

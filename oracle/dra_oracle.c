@@ -1,0 +1,446 @@
+/*
+ * dra_oracle.c — plain-C restatement of spec/ALLOCATION.md.  TEST INFRASTRUCTURE ONLY (see dra_oracle.h).
+ *
+ * PARITY UNPINNED for the claim search: the reference has no implementation of it to follow
+ * (SURVEY.md F1).  Every rule the reference DOES fix is cited where it is restated.
+ * Written for obviousness, not speed: one GPU at a time, one start at a time, no bit tricks shared with
+ * the CUDA kernels (the kernels use SWAR shifts, ballots and monotone "dead profile" shortcuts; this
+ * file uses none of them, so agreement between the two is evidence, not tautology).
+ */
+#include "dra_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------ */
+
+static void put(dra_out_rec* o, uint32_t gpu, uint8_t start, uint8_t size, uint8_t profile, uint8_t st)
+{
+    o->gpu = gpu; o->start = start; o->size = size; o->profile = profile; o->status = st;
+}
+
+static uint8_t out_profile(const dra_claim_rec* c)
+{
+    if (c->kind == DRA_KIND_GPU) return DRA_PROFILE_GPU;
+    if (c->kind == DRA_KIND_SHARED) return DRA_PROFILE_SHARED;
+    return c->profile;
+}
+
+/* spec §3 */
+static int claim_invalid(const dra_claim_rec* c, uint32_t n_node, int have_off)
+{
+    if (c->kind > DRA_KIND_SHARED) return 1;
+    if (c->node >= n_node) return 1;
+    if (c->kind == DRA_KIND_GPU) {
+        if (c->count == 0 || c->count > DRA_MAX_COUNT) return 1;
+        if (!have_off && c->count != 1) return 1;
+    }
+    if (c->kind == DRA_KIND_MIG && c->profile >= DRA_MAX_PROFILES) return 1;
+    return 0;
+}
+
+/* spec §1: slots(c) */
+static uint32_t claim_slots(const dra_claim_rec* c, uint32_t n_node, int have_off)
+{
+    if (claim_invalid(c, n_node, have_off)) return 1;
+    return c->kind == DRA_KIND_GPU ? c->count : 1;
+}
+
+static void fail_all(dra_out_rec* o, uint32_t slots, const dra_claim_rec* c, uint8_t st)
+{
+    for (uint32_t k = 0; k < slots; k++) put(&o[k], DRA_GPU_NONE, 0, 0, out_profile(c), st);
+}
+
+/* Lowest start of entry e that fits into `busy`; -1 when none.
+ * Overlap rule: a placement occupies memory slices [start, start+size) and two placements conflict iff
+ * the ranges intersect — go-nvml nvml.h:9761-9765 and :10079-10082, published per slice by
+ * cmd/nvidia-dra-plugin/deviceinfo.go:199-204. */
+static int lowest_fit(uint16_t busy, dra_prof_ent e)
+{
+    for (int s = 0; s < 16; s++) {
+        if (!((e.start_mask >> s) & 1u)) continue;
+        uint32_t m = ((1u << e.size) - 1u) << s;
+        if ((busy & m) == 0) return s;
+    }
+    return -1;
+}
+
+static int gpu_offers(const dra_gpu_rec* g, dra_prof_ent e)
+{
+    /* MIG devices exist only under MIG-enabled parents: cmd/nvidia-dra-plugin/nvlib.go:316-318 */
+    return (g->flags & DRA_GPU_MIG_ENABLED) && !(g->flags & DRA_GPU_UNAVAILABLE) && e.start_mask != 0;
+}
+
+typedef struct node_job {
+    dra_gpu_rec* gpus;          /* the node's GPUs */
+    uint32_t g0, ng;            /* global index of gpus[0], count */
+    const dra_profile_tbl* tbl;
+    const dra_claim_rec* claims;
+    const uint32_t* idx;        /* the node's claims, input order */
+    uint32_t cnt;
+    uint32_t n_node;
+    const uint32_t* out_off;    /* may be NULL */
+    dra_out_rec* out;
+    int commit;                 /* 0: evaluate only (UnsuitableNodes) — caller passes a scratch copy */
+    int all_ok;                 /* out: every slot OK */
+    uint32_t node_override;     /* UnsuitableNodes: claim.node := candidate */
+    int use_override;
+} node_job;
+
+static dra_out_rec* slot_of(const node_job* j, uint32_t ci)
+{
+    return &j->out[j->out_off ? j->out_off[ci] : ci];
+}
+
+/* spec §4 — full GPUs are published only for GPUs that are not MIG-enabled: nvlib.go:152 */
+static void do_gpu(node_job* j, uint32_t ci)
+{
+    const dra_claim_rec* c = &j->claims[ci];
+    dra_out_rec* o = slot_of(j, ci);
+    uint32_t elig = 0;
+    for (uint32_t g = 0; g < j->ng; g++) {
+        const dra_gpu_rec* r = &j->gpus[g];
+        if (!(r->flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE)) &&
+            r->share_cnt == 0) elig++;
+    }
+    if (elig < c->count) { fail_all(o, c->count, c, DRA_ST_NO_CAPACITY); j->all_ok = 0; return; }
+    uint32_t k = 0;
+    for (uint32_t g = 0; g < j->ng && k < c->count; g++) {
+        dra_gpu_rec* r = &j->gpus[g];
+        if (!(r->flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE)) &&
+            r->share_cnt == 0) {
+            r->flags |= DRA_GPU_FULL_ALLOCATED;
+            put(&o[k++], j->g0 + g, 0, 0, DRA_PROFILE_GPU, DRA_ST_OK);
+        }
+    }
+}
+
+/* spec §5 */
+static void do_mig(node_job* j, uint32_t ci)
+{
+    const dra_claim_rec* c = &j->claims[ci];
+    dra_out_rec* o = slot_of(j, ci);
+    int any_offer = 0;
+    for (uint32_t g = 0; g < j->ng; g++) {
+        dra_gpu_rec* r = &j->gpus[g];
+        dra_prof_ent e = j->tbl[r->model].ent[c->profile];
+        if (!gpu_offers(r, e)) continue;
+        any_offer = 1;
+        if (r->flags & DRA_GPU_FULL_ALLOCATED) continue;
+        int s = lowest_fit(r->busy, e);
+        if (s < 0) continue;
+        r->busy |= (uint16_t)(((1u << e.size) - 1u) << s);
+        put(o, j->g0 + g, (uint8_t)s, e.size, c->profile, DRA_ST_OK);
+        return;
+    }
+    put(o, DRA_GPU_NONE, 0, 0, c->profile, any_offer ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE);
+    j->all_ok = 0;
+}
+
+/* spec §6 — matchAttribute parentUUID: demo/specs/quickstart/gpu-test4.yaml:42-44 */
+static void do_group(node_job* j, uint32_t i0, uint32_t i1)
+{
+    for (uint32_t g = 0; g < j->ng; g++) {
+        dra_gpu_rec* r = &j->gpus[g];
+        if (!(r->flags & DRA_GPU_MIG_ENABLED)) continue;
+        if (r->flags & (DRA_GPU_UNAVAILABLE | DRA_GPU_FULL_ALLOCATED)) continue;
+        uint16_t busy = r->busy;
+        int starts[DRA_MAX_GROUP];
+        int ok = 1;
+        for (uint32_t i = i0; i < i1 && ok; i++) {
+            const dra_claim_rec* c = &j->claims[j->idx[i]];
+            dra_prof_ent e = j->tbl[r->model].ent[c->profile];
+            int s = e.start_mask ? lowest_fit(busy, e) : -1;
+            if (s < 0) { ok = 0; break; }
+            starts[i - i0] = s;
+            busy |= (uint16_t)(((1u << e.size) - 1u) << s);
+        }
+        if (!ok) continue;
+        r->busy = busy;
+        for (uint32_t i = i0; i < i1; i++) {
+            const dra_claim_rec* c = &j->claims[j->idx[i]];
+            dra_prof_ent e = j->tbl[r->model].ent[c->profile];
+            put(slot_of(j, j->idx[i]), j->g0 + g, (uint8_t)starts[i - i0], e.size, c->profile, DRA_ST_OK);
+        }
+        return;
+    }
+    for (uint32_t i = i0; i < i1; i++) {
+        const dra_claim_rec* c = &j->claims[j->idx[i]];
+        put(slot_of(j, j->idx[i]), DRA_GPU_NONE, 0, 0, c->profile, DRA_ST_GROUP);
+    }
+    j->all_ok = 0;
+}
+
+/* spec §7 (extension) */
+static void do_shared(node_job* j, uint32_t ci)
+{
+    const dra_claim_rec* c = &j->claims[ci];
+    dra_out_rec* o = slot_of(j, ci);
+    for (uint32_t g = 0; g < j->ng; g++) {
+        dra_gpu_rec* r = &j->gpus[g];
+        if (r->flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE)) continue;
+        if (r->share_cnt == 0xFFFFu) continue;
+        if (r->mem_free_mib < c->mem_limit_mib) continue;
+        r->mem_free_mib -= c->mem_limit_mib;
+        r->share_cnt++;
+        put(o, j->g0 + g, 0, 0, DRA_PROFILE_SHARED, DRA_ST_OK);
+        return;
+    }
+    put(o, DRA_GPU_NONE, 0, 0, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT);
+    j->all_ok = 0;
+}
+
+static int in_run(const node_job* j, uint32_t i, uint32_t group, int have_off)
+{
+    const dra_claim_rec* c = &j->claims[j->idx[i]];
+    dra_claim_rec t = *c;
+    if (j->use_override) t.node = j->node_override;
+    return t.kind == DRA_KIND_MIG && t.group == group && !claim_invalid(&t, j->n_node, have_off);
+}
+
+/* spec §2: the node's claims, sequentially, input order */
+static void node_process(node_job* j)
+{
+    int have_off = j->out_off != NULL;
+    j->all_ok = 1;
+    uint32_t i = 0;
+    while (i < j->cnt) {
+        uint32_t ci = j->idx[i];
+        dra_claim_rec c = j->claims[ci];
+        if (j->use_override) c.node = j->node_override;
+        if (claim_invalid(&c, j->n_node, have_off)) {
+            put(slot_of(j, ci), DRA_GPU_NONE, 0, 0, out_profile(&c), DRA_ST_INVALID);
+            j->all_ok = 0; i++; continue;
+        }
+        if (c.kind == DRA_KIND_MIG && c.group != 0) {
+            uint32_t e = i + 1;
+            while (e < j->cnt && e - i < DRA_MAX_GROUP && in_run(j, e, c.group, have_off)) e++;
+            do_group(j, i, e);
+            i = e; continue;
+        }
+        if (c.kind == DRA_KIND_GPU) do_gpu(j, ci);
+        else if (c.kind == DRA_KIND_MIG) do_mig(j, ci);
+        else do_shared(j, ci);
+        i++;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+
+static int check_inventory(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off,
+                           uint32_t n_node, const dra_profile_tbl* tbl)
+{
+    if (node_off[0] != 0 || node_off[n_node] != n_gpu) return -1;
+    for (uint32_t n = 0; n < n_node; n++) {
+        if (node_off[n + 1] < node_off[n]) return -1;
+        if (node_off[n + 1] - node_off[n] > DRA_MAX_GPUS_PER_NODE) return -1;
+        for (uint32_t g = node_off[n]; g < node_off[n + 1]; g++) {
+            if (gpus[g].model >= DRA_MAX_MODELS) return -1;
+            if (gpus[g].node != n) return -1;
+        }
+    }
+    for (uint32_t m = 0; m < DRA_MAX_MODELS; m++)
+        for (uint32_t p = 0; p < DRA_MAX_PROFILES; p++) {
+            dra_prof_ent e = tbl[m].ent[p];
+            if (!e.start_mask) continue;
+            if (e.size < 1 || e.size > 16) return -1;
+            int hi = 15; while (!((e.start_mask >> hi) & 1u)) hi--;
+            if (hi + e.size > 16) return -1;
+        }
+    return 0;
+}
+
+typedef struct bucketed {
+    uint32_t* idx;       /* claim indices, stable by node */
+    uint32_t* off;       /* n_node+1 */
+} bucketed;
+
+/* stable counting sort of claim indices by node (spec §2); claims with node >= n_node are left out */
+static int bucket(const dra_claim_rec* claims, uint32_t n_claim, uint32_t n_node, bucketed* b)
+{
+    b->off = (uint32_t*)calloc((size_t)n_node + 2, sizeof(uint32_t));
+    b->idx = (uint32_t*)malloc(((size_t)n_claim + 1) * sizeof(uint32_t));
+    if (!b->off || !b->idx) return -1;
+    for (uint32_t i = 0; i < n_claim; i++)
+        if (claims[i].node < n_node) b->off[claims[i].node + 1]++;
+    for (uint32_t n = 0; n < n_node; n++) b->off[n + 1] += b->off[n];
+    uint32_t* cur = (uint32_t*)malloc(((size_t)n_node + 1) * sizeof(uint32_t));
+    if (!cur) return -1;
+    memcpy(cur, b->off, ((size_t)n_node + 1) * sizeof(uint32_t));
+    for (uint32_t i = 0; i < n_claim; i++)
+        if (claims[i].node < n_node) b->idx[cur[claims[i].node]++] = i;
+    free(cur);
+    return 0;
+}
+
+typedef struct mt_arg {
+    dra_gpu_rec* gpus; const uint32_t* node_off; uint32_t n_node;
+    const dra_profile_tbl* tbl; const dra_claim_rec* claims;
+    const bucketed* b; const uint32_t* out_off; dra_out_rec* out;
+    uint32_t n0, n1;
+} mt_arg;
+
+static void run_nodes(const mt_arg* a)
+{
+    for (uint32_t n = a->n0; n < a->n1; n++) {
+        node_job j;
+        memset(&j, 0, sizeof j);
+        j.gpus = a->gpus + a->node_off[n];
+        j.g0 = a->node_off[n];
+        j.ng = a->node_off[n + 1] - a->node_off[n];
+        j.tbl = a->tbl; j.claims = a->claims;
+        j.idx = a->b->idx + a->b->off[n];
+        j.cnt = a->b->off[n + 1] - a->b->off[n];
+        j.n_node = a->n_node; j.out_off = a->out_off; j.out = a->out; j.commit = 1;
+        node_process(&j);
+    }
+}
+
+static void* mt_entry(void* p) { run_nodes((const mt_arg*)p); return NULL; }
+
+int dra_oracle_allocate_mt(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node,
+                           const dra_profile_tbl* tbl,
+                           const dra_claim_rec* claims, uint32_t n_claim,
+                           const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, int n_threads)
+{
+    if (check_inventory(gpus, n_gpu, node_off, n_node, tbl)) return -1;
+    int have_off = out_off != NULL;
+    for (uint32_t i = 0; i < n_claim; i++) {
+        uint32_t base = have_off ? out_off[i] : i;
+        uint32_t sl = claim_slots(&claims[i], n_node, have_off);
+        if (base > n_out || sl > n_out - base) return -1;
+    }
+    /* claims that name no node of the inventory: INVALID, no state touched (spec §3) */
+    for (uint32_t i = 0; i < n_claim; i++)
+        if (claims[i].node >= n_node)
+            put(&out[have_off ? out_off[i] : i], DRA_GPU_NONE, 0, 0, out_profile(&claims[i]), DRA_ST_INVALID);
+
+    bucketed b;
+    if (bucket(claims, n_claim, n_node, &b)) return -1;
+
+    mt_arg base = { gpus, node_off, n_node, tbl, claims, &b, out_off, out, 0, n_node };
+    if (n_threads <= 1 || n_node < 2) {
+        run_nodes(&base);
+    } else {
+        if ((uint32_t)n_threads > n_node) n_threads = (int)n_node;
+        pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+        mt_arg* args = (mt_arg*)malloc(sizeof(mt_arg) * (size_t)n_threads);
+        /* contiguous node ranges balanced by claim count */
+        uint32_t n = 0;
+        for (int t = 0; t < n_threads; t++) {
+            args[t] = base;
+            args[t].n0 = n;
+            uint64_t target = (uint64_t)b.off[n_node] * (uint64_t)(t + 1) / (uint64_t)n_threads;
+            while (n < n_node && (b.off[n + 1] <= target || t == n_threads - 1)) n++;
+            if (t == n_threads - 1) n = n_node;
+            args[t].n1 = n;
+            pthread_create(&th[t], NULL, mt_entry, &args[t]);
+        }
+        for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+        free(th); free(args);
+    }
+    free(b.idx); free(b.off);
+    return 0;
+}
+
+int dra_oracle_allocate(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node,
+                        const dra_profile_tbl* tbl,
+                        const dra_claim_rec* claims, uint32_t n_claim,
+                        const uint32_t* out_off, dra_out_rec* out, uint32_t n_out)
+{
+    return dra_oracle_allocate_mt(gpus, n_gpu, node_off, n_node, tbl, claims, n_claim, out_off, out,
+                                  n_out, 1);
+}
+
+/* spec §8 — all-or-nothing per pod on a snapshot of the candidate node */
+int dra_oracle_unsuitable(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off,
+                          uint32_t n_node, const dra_profile_tbl* tbl,
+                          const dra_claim_rec* claims, uint32_t n_claim,
+                          const uint32_t* pod_off, uint32_t n_pod,
+                          const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits)
+{
+    if (check_inventory(gpus, n_gpu, node_off, n_node, tbl)) return -1;
+    if (pod_off[n_pod] != n_claim) return -1;
+    uint32_t n_pair = cand_off[n_pod];
+    memset(suitable_bits, 0, ((size_t)n_pair + 7) / 8);
+
+    /* scratch: per-claim slot offsets (prefix of slots) and a scratch out array */
+    uint32_t* soff = (uint32_t*)malloc(((size_t)n_claim + 1) * sizeof(uint32_t));
+    uint32_t* idx = (uint32_t*)malloc(((size_t)n_claim + 1) * sizeof(uint32_t));
+    if (!soff || !idx) return -1;
+    for (uint32_t i = 0; i < n_claim; i++) idx[i] = i;
+
+    for (uint32_t p = 0; p < n_pod; p++) {
+        uint32_t c0 = pod_off[p], c1 = pod_off[p + 1];
+        for (uint32_t k = cand_off[p]; k < cand_off[p + 1]; k++) {
+            uint32_t n = cand_nodes[k];
+            if (n >= n_node) continue;                       /* unknown node: unsuitable */
+            uint32_t tot = 0;
+            for (uint32_t i = c0; i < c1; i++) {
+                dra_claim_rec t = claims[i]; t.node = n;
+                soff[i] = tot; tot += claim_slots(&t, n_node, 1);
+            }
+            dra_out_rec* scratch = (dra_out_rec*)malloc(((size_t)tot + 1) * sizeof(dra_out_rec));
+            dra_gpu_rec snap[DRA_MAX_GPUS_PER_NODE];
+            uint32_t ng = node_off[n + 1] - node_off[n];
+            memcpy(snap, gpus + node_off[n], ng * sizeof(dra_gpu_rec));
+            node_job j;
+            memset(&j, 0, sizeof j);
+            j.gpus = snap; j.g0 = node_off[n]; j.ng = ng; j.tbl = tbl; j.claims = claims;
+            j.idx = idx + c0; j.cnt = c1 - c0; j.n_node = n_node;
+            j.out_off = soff; j.out = scratch;
+            j.use_override = 1; j.node_override = n;
+            node_process(&j);
+            if (j.all_ok) suitable_bits[k >> 3] |= (uint8_t)(1u << (k & 7));
+            free(scratch);
+        }
+    }
+    free(soff); free(idx);
+    return 0;
+}
+
+/* spec §9 */
+int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu,
+                          const dra_claim_rec* claims, uint32_t n_claim,
+                          const uint32_t* out_off, const dra_out_rec* out, uint32_t n_out)
+{
+    int have_off = out_off != NULL;
+    for (uint32_t i = 0; i < n_claim; i++) {
+        const dra_claim_rec* c = &claims[i];
+        uint32_t base = have_off ? out_off[i] : i;
+        uint32_t sl = (c->kind == DRA_KIND_GPU && c->count >= 1 && c->count <= DRA_MAX_COUNT &&
+                       (have_off || c->count == 1)) ? c->count : 1;
+        if (base > n_out || sl > n_out - base) return -1;
+        for (uint32_t k = 0; k < sl; k++) {
+            const dra_out_rec* o = &out[base + k];
+            if (o->status != DRA_ST_OK || o->gpu >= n_gpu) continue;
+            dra_gpu_rec* r = &gpus[o->gpu];
+            if (c->kind == DRA_KIND_GPU) r->flags &= (uint8_t)~DRA_GPU_FULL_ALLOCATED;
+            else if (c->kind == DRA_KIND_MIG)
+                r->busy &= (uint16_t)~(((1u << o->size) - 1u) << o->start);
+            else if (c->kind == DRA_KIND_SHARED) { r->mem_free_mib += c->mem_limit_mib; r->share_cnt--; }
+        }
+    }
+    return 0;
+}
+
+/* api/nvidia.com/resource/gpu/v1alpha1/sharing.go:234-237:
+ *     v := d.Value() / 1024 / 1024 ; return fmt.Sprintf("%vM", v), v > 0          */
+int64_t dra_oracle_megabyte(int64_t bytes, int* valid)
+{
+    int64_t v = bytes / 1024 / 1024;     /* C99 '/' truncates toward zero, as Go's does */
+    if (valid) *valid = v > 0;
+    return v;
+}
+
+/* cmd/nvidia-dra-controller/imex.go:336-349 */
+int32_t dra_oracle_imex_offset(const int32_t* used, uint32_t n_used, int32_t step, int32_t limit)
+{
+    for (int32_t off = 0; off < limit; off += step) {
+        int taken = 0;
+        for (uint32_t k = 0; k < n_used; k++) if (used[k] == off) { taken = 1; break; }
+        if (!taken) return off;
+    }
+    return -1;
+}

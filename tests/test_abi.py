@@ -1,0 +1,91 @@
+"""CPU suite, part 2: the C-ABI library builds, loads, and exports every symbol include/dra_alloc.h
+declares; record layouts match; with no GPU the library refuses to create a context (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dra_alloc.h")
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dra_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.api.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dra_alloc.h but not exported"
+    assert set(names) == set(pkg.api.SYMBOLS), "python binding and header drifted apart"
+    assert lib.dra_abi_version() == 1
+
+
+def test_record_sizes_match_header(pkg, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include "dra_alloc.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dra_gpu_rec), sizeof(dra_claim_rec),'
+                   'sizeof(dra_out_rec), sizeof(dra_prof_ent), sizeof(dra_profile_tbl),'
+                   'offsetof(dra_gpu_rec, share_cnt), offsetof(dra_claim_rec, group));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    R = pkg.records
+    assert [int(x) for x in got] == [R.GPU_DTYPE.itemsize, R.CLAIM_DTYPE.itemsize, R.OUT_DTYPE.itemsize,
+                                     R.PROF_DTYPE.itemsize, 64, R.GPU_DTYPE.fields["share_cnt"][1],
+                                     R.CLAIM_DTYPE.fields["group"][1]]
+
+
+def test_no_gpu_means_no_context(pkg):
+    """Without a CUDA device dra_ctx_create must fail loudly — the product has no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present; covered by the gpu suite")
+    with pytest.raises(pkg.api.DraError) as e:
+        pkg.api.Context(device=0)
+    assert e.value.code == pkg.api.E_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_touch_the_oracle():
+    """oracle/ is a checker: nothing under the product package may import, link or mention it."""
+    pk = os.path.join(ROOT, "k8s-dra-driver_b200")
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert "dra_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+    so = os.path.join(pk, "libdra_alloc.so")
+    if os.path.exists(so):
+        out = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+        assert "dra_oracle" not in out
+
+
+def test_kernels_are_sm100a_and_use_tma(pkg):
+    """cuobjdump evidence: the cubin is sm_100a, TMA bulk copies (UBLKCP), ballots (VOTE), MATCH are in SASS."""
+    so = pkg.api.SO_PATH
+    r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in r.stdout
+    for mnem in ("UBLKCP", "VOTE", "MATCH.ANY", "SYNCS"):
+        assert mnem in r.stdout, mnem
+
+
+def test_synthetic_configs_shape(pkg):
+    S = pkg.synth
+    w = S.cfg2()
+    assert (w.n_claim, w.n_gpu, w.n_node) == (10_000, 1000, 125)
+    assert w.algorithmic_bytes() == 24 * 10_000 + 16 * 1000          # 256,000 B
+    frac = np.bincount(w.claims["profile"], minlength=5) / w.n_claim
+    assert abs(frac[0] - .4) < .02 and abs(frac[1] - .3) < .02 and abs(frac[2] - .2) < .02 and abs(frac[4] - .1) < .02
+    w5 = S.cfg5()
+    assert (w5.n_claim, w5.n_gpu) == (50_000, 512) and np.all(w5.gpus["busy"] != 0xFF)
+    assert S.cfg2().claims.tobytes() == w.claims.tobytes()           # seeded: reproducible

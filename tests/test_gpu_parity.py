@@ -1,0 +1,210 @@
+"""GPU suite: the CUDA path through the C ABI must be BIT-EXACT with the CPU oracle (integer work)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(ctx, w, flags=0, sort=False):
+    ctx.set_table(w.table)
+    ctx.set_inventory(w.gpus, w.node_off)
+    out = ctx.allocate(w.claims, w.out_off, w.n_out, flags=flags)
+    return out, ctx.get_inventory()
+
+
+def _assert_same(out, inv, ref_out, ref_inv, what=""):
+    if out.tobytes() != ref_out.tobytes():
+        bad = np.nonzero(out.view(np.uint64) != ref_out.view(np.uint64))[0]
+        raise AssertionError(f"{what}: {len(bad)} OutRecs differ, first at {bad[0]}: cuda={out[bad[0]]} oracle={ref_out[bad[0]]}")
+    if inv.tobytes() != ref_inv.tobytes():
+        bad = np.nonzero(inv.view("V16") != ref_inv.view("V16"))[0]
+        raise AssertionError(f"{what}: inventory differs at gpu {bad[0]}: cuda={inv[bad[0]]} oracle={ref_inv[bad[0]]}")
+
+
+# ---- frozen golden fixtures: no oracle needed on the box -------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_matches_golden(pkg, ctx, name):
+    g = load_golden(name)
+    ctx.set_table(g["table"])
+    ctx.set_inventory(g["gpus"], g["node_off"])
+    out = ctx.allocate(g["claims"], g["out_off"], len(g["out"]))
+    _assert_same(out, ctx.get_inventory(), g["out"], g["gpus_after"], name)
+
+
+# ---- every BASELINE config at full size, against the oracle ----------------------------------------
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_cuda_matches_oracle_on_baseline_configs(pkg, ctx, oracle, cfg):
+    w = pkg.synth.CONFIGS[cfg]()
+    out, inv = _run(ctx, w)
+    ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+    _assert_same(out, inv, ref_out, ref_inv, cfg)
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg5"])
+def test_node_sorted_fast_path(pkg, ctx, oracle, cfg):
+    w = pkg.synth.CONFIGS[cfg]().node_sorted()
+    out, inv = _run(ctx, w, flags=pkg.api.F_NODE_SORTED)
+    ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+    _assert_same(out, inv, ref_out, ref_inv, cfg + " sorted")
+
+
+def test_node_sorted_flag_is_verified(pkg, ctx):
+    w = pkg.synth.cfg2(2000, 20)           # generation order: not sorted
+    ctx.set_table(w.table)
+    ctx.set_inventory(w.gpus, w.node_off)
+    with pytest.raises(pkg.api.DraError) as e:
+        ctx.allocate(w.claims, flags=pkg.api.F_NODE_SORTED)
+    assert e.value.code == pkg.api.E_INVAL
+    assert ctx.get_inventory().tobytes() == w.gpus.tobytes()      # nothing changed
+    # and the context is still usable
+    out = ctx.allocate(w.claims)
+    assert (out["status"] == 0).any()
+
+
+# ---- fuzz: ragged heterogeneous nodes, all kinds, counts, groups, malformed claims ------------------
+@pytest.mark.parametrize("seed", range(12))
+def test_cuda_matches_oracle_fuzz(pkg, ctx, oracle, seed):
+    n_claim = [50, 333, 1000, 4000, 9000, 20000][seed % 6]
+    n_node = [1, 3, 17, 64, 200, 501][(seed * 5) % 6]
+    w = pkg.synth.mixed(n_claim, n_node, 100 + seed, invalid=seed % 3 != 0)
+    out, inv = _run(ctx, w)
+    ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+    _assert_same(out, inv, ref_out, ref_inv, f"mixed seed {seed}")
+
+
+def test_edge_cases(pkg, ctx, oracle):
+    R = pkg.records
+    t = R.default_table()
+    # empty batch
+    g, off = R.make_inventory([8, 8], mig=True)
+    ctx.set_table(t); ctx.set_inventory(g, off)
+    assert len(ctx.allocate(np.zeros(0, dtype=R.CLAIM_DTYPE))) == 0
+    assert ctx.get_inventory().tobytes() == g.tobytes()
+    # empty inventory (nodes without GPUs), every claim fails the way the oracle says
+    g0, off0 = R.make_inventory([0, 0, 0], mig=True)
+    w = pkg.synth.mixed(300, 3, 5)
+    w.gpus, w.node_off = g0, off0
+    out, inv = _run(ctx, w)
+    ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+    _assert_same(out, inv, ref_out, ref_inv, "empty inventory")
+    # one node, one claim; maximum node width (32 GPUs); a run of exactly 32 and of 33 members
+    g, off = R.make_inventory([32], mig=True)
+    c = np.zeros(1 + 32 + 33, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_MIG; c["count"] = 1; c["profile"] = R.GI_1_SLICE
+    c["group"][1:33] = 5; c["group"][33:] = 6
+    ctx.set_inventory(g, off)
+    out = ctx.allocate(c)
+    ref_out, ref_inv = oracle.allocate(g, off, t, c)
+    _assert_same(out, ctx.get_inventory(), ref_out, ref_inv, "wide node + long runs")
+    # all claims on a single node out of many (one long sequential chain, > one TMA ring)
+    w = pkg.synth.cfg2(5000, 40)
+    w.claims["node"] = 7
+    out, inv = _run(ctx, w)
+    ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims)
+    _assert_same(out, inv, ref_out, ref_inv, "single hot node")
+
+
+def test_out_off_out_of_range_is_an_error(pkg, ctx):
+    R = pkg.records
+    g, off = R.make_inventory([4], mig=False)
+    c = np.zeros(2, dtype=R.CLAIM_DTYPE); c["kind"] = R.KIND_GPU; c["count"] = 2
+    ctx.set_table(R.default_table()); ctx.set_inventory(g, off)
+    with pytest.raises(pkg.api.DraError):
+        ctx.allocate(c, out_off=np.array([0, 3], np.uint32), n_out=4)
+
+
+# ---- state across batches, deallocate round trip ----------------------------------------------------
+def test_batches_accumulate_and_deallocate_round_trips(pkg, ctx, oracle):
+    w = pkg.synth.mixed(6000, 50, 42, invalid=False)
+    ctx.set_table(w.table); ctx.set_inventory(w.gpus, w.node_off)
+    half = len(w.claims) // 2
+    c1, c2 = w.claims[:half], w.claims[half:]
+    o1, n1 = pkg.records.out_offsets(c1, w.n_node)
+    o2, n2 = pkg.records.out_offsets(c2, w.n_node)
+    out1 = ctx.allocate(c1, o1, n1)
+    out2 = ctx.allocate(c2, o2, n2)
+    r1, gi = oracle.allocate(w.gpus, w.node_off, w.table, c1, o1, n1)
+    r2, gj = oracle.allocate(gi, w.node_off, w.table, c2, o2, n2)
+    _assert_same(out1, ctx.get_inventory(), r1, gj, "batch 1")
+    assert out2.tobytes() == r2.tobytes()
+    ctx.deallocate(c2, out2, o2)
+    assert ctx.get_inventory().tobytes() == gi.tobytes()
+    ctx.deallocate(c1, out1, o1)
+    assert ctx.get_inventory().tobytes() == w.gpus.tobytes()
+    # FRESH_INVENTORY evaluates against the loaded inventory regardless of what happened since
+    out1b = ctx.allocate(c1, o1, n1)
+    out1c = ctx.allocate(c1, o1, n1, flags=pkg.api.F_FRESH_INVENTORY)
+    assert out1c.tobytes() == r1.tobytes() and out1b.tobytes() == r1.tobytes()
+    assert ctx.get_inventory().tobytes() == gi.tobytes()
+
+
+# ---- size-independent properties at full BASELINE sizes ----------------------------------------------
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg5"])
+def test_properties_at_full_size(pkg, ctx, cfg):
+    R = pkg.records
+    w = pkg.synth.CONFIGS[cfg]()
+    out, inv = _run(ctx, w)
+    ok = out["status"] == 0
+    # 1. conservation: slices newly occupied == sum of sizes of successful MIG claims
+    newly = (inv["busy"] & ~w.gpus["busy"])
+    pop = np.array([bin(int(x)).count("1") for x in newly]).sum()
+    assert pop == int(out["size"][ok].sum())
+    # 2. no overlap: per GPU, the placements handed out are pairwise disjoint and avoid the initial busy mask
+    masks = ((1 << out["size"][ok].astype(np.int64)) - 1) << out["start"][ok].astype(np.int64)
+    acc = w.gpus["busy"].astype(np.int64).copy()
+    for gidx, m in zip(out["gpu"][ok], masks):
+        assert acc[gidx] & m == 0
+        acc[gidx] |= m
+    assert np.array_equal(acc, inv["busy"].astype(np.int64))
+    # 3. every placement is one the table offers, on a GPU of the claim's node
+    node_of = w.gpus["node"][out["gpu"][ok]]
+    assert np.array_equal(node_of, w.claims["node"][ok])
+    ent = w.table[0][out["profile"][ok]]
+    assert np.all((ent["start_mask"] >> out["start"][ok]) & 1) and np.array_equal(ent["size"], out["size"][ok])
+    # 4. first-fit fixed point: replaying the failed claims against the final inventory still fails them all
+    failed = w.claims[~ok]
+    ctx.set_inventory(inv, w.node_off)
+    again = ctx.allocate(failed)
+    assert not (again["status"] == 0).any()
+    # 5. deallocate everything -> initial inventory
+    ctx.deallocate(w.claims, out)
+    assert ctx.get_inventory().tobytes() == w.gpus.tobytes()
+
+
+# ---- UnsuitableNodes ------------------------------------------------------------------------------------
+def test_unsuitable_matches_oracle(pkg, ctx, oracle):
+    R = pkg.records
+    rng = np.random.default_rng(7)
+    w = pkg.synth.mixed(3000, 40, 77, invalid=False)
+    # pods of 1..4 claims; each with 1..12 candidate nodes (a few unknown)
+    sizes = rng.integers(1, 5, size=3000)
+    pod_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    pod_off = pod_off[pod_off <= len(w.claims)]
+    if pod_off[-1] != len(w.claims):
+        pod_off = np.append(pod_off, len(w.claims)).astype(np.uint32)
+    n_pod = len(pod_off) - 1
+    ncand = rng.integers(1, 13, size=n_pod)
+    cand_off = np.concatenate([[0], np.cumsum(ncand)]).astype(np.uint32)
+    cand_nodes = rng.integers(0, w.n_node + 2, size=int(cand_off[-1])).astype(np.uint32)
+    # partially filled inventory makes the answer interesting
+    _, inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims[:800], w.out_off[:800], int(w.out_off[800]))
+    ctx.set_table(w.table); ctx.set_inventory(inv, w.node_off)
+    got = ctx.unsuitable(w.claims, pod_off, cand_nodes, cand_off)
+    ref = oracle.unsuitable(inv, w.node_off, w.table, w.claims, pod_off, cand_nodes, cand_off)
+    assert got.tobytes() == ref.tobytes()
+    assert 0 < np.unpackbits(got).sum() < int(cand_off[-1])
+    assert ctx.get_inventory().tobytes() == inv.tobytes()      # pure
+
+
+def test_launch_counter_counts_our_kernels(pkg, ctx):
+    w = pkg.synth.cfg2(1000, 10)
+    ctx.set_table(w.table); ctx.set_inventory(w.gpus, w.node_off)
+    before = ctx.launch_count()
+    ctx.allocate(w.claims)
+    assert ctx.launch_count() - before == 4          # hist, scan, scatter, pack
+    ctx.set_inventory(w.gpus, w.node_off)
+    before = ctx.launch_count()
+    ctx.allocate(w.node_sorted().claims, flags=pkg.api.F_NODE_SORTED)
+    assert ctx.launch_count() - before == 2          # sorted_prep, pack
