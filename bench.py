@@ -187,7 +187,10 @@ def run_ours(args):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything (flush, events, our kernels): the legacy default stream's handle is
+    # 0, which the C ABI reads as "create your own stream", and events on another stream would time nothing
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     w = workload(pkg, rank, world)
     n_claim, n_out = w.n_claim, w.n_out

@@ -1,0 +1,60 @@
+"""Turns gpurun_out ncu artefacts into the small text summaries committed under profiles/.
+
+  python profiles/summarize.py launches gpurun_out/launches_r01.csv            > profiles/r01_launches.txt
+  python profiles/summarize.py kernel   gpurun_out/prof_pack_r01.ncu-rep       > profiles/r01_k_pack.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic",
+        "sm__cycles_elapsed.max", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warp_latency_per_inst_issued.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio"]
+
+
+def launches(path):
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    hdr = rows[0]
+    ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            agg.setdefault(r[ik].split("(")[0][:60], []).append(float(r[iv].replace(",", "")))
+        except ValueError:
+            pass
+    ours = {k: v for k, v in agg.items() if "dra::" in k}
+    tot = sum(sum(v) / len(v) for v in ours.values())
+    print(f"# ncu --metrics gpu__time_duration.sum --clock-control none  ({path})")
+    print("# per-launch device time, cold-cache and serialised: compare SHARES of the step, not absolutes")
+    print(f"{'kernel':<62}{'launches':>9}{'avg us':>10}{'min us':>10}{'share':>8}")
+    for k, v in agg.items():
+        a = sum(v) / len(v) / 1e3
+        sh = f"{100 * a * 1e3 / tot:6.1f}%" if k in ours else "   (not ours)"
+        print(f"{k:<62}{len(v):>9}{a:>10.2f}{min(v) / 1e3:>10.2f}{sh:>8}")
+
+
+def kernel(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f"# ncu --set full --clock-control none --import-source on  ({path})")
+    for r in rows[2:]:
+        print(f"\n== {r[hdr.index('Kernel Name')]}  (launch id {r[hdr.index('ID')]})")
+        for k in KEYS:
+            if k in hdr:
+                print(f"  {k:<86}{r[hdr.index(k)]:>16} {units[hdr.index(k)]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
