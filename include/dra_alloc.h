@@ -117,6 +117,7 @@ typedef struct dra_cfg {
 } dra_cfg;
 
 #define DRA_CFG_USE_GRAPH  0x1u  /* replay the kernel chain as one CUDA graph (host-buffer calls) */
+#define DRA_CFG_NO_FUSED   0x2u  /* never take the single-launch path (always bucket + pack); for tests */
 
 /* error codes (negative) */
 #define DRA_OK        0

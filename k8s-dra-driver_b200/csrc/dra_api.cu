@@ -102,7 +102,8 @@ struct dra_ctx {
     cudaEvent_t ev[8] = {};
     bool ev_ok = false;
     float timings[5] = {0, 0, 0, 0, 0};
-    int hist_smem_set = 0;
+    int hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0;
+    uint64_t fused_max_work = 6000000ull;   // n_node * n_claim up to which the single-launch kernel is used
 
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -206,6 +207,36 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     Err err = err_of(ctx);
     Prof prof(ctx);
 
+    PackArgs a;
+    memset(&a, 0, sizeof a);
+    a.inv_src = (flags & DRA_F_FRESH_INVENTORY) ? ctx->d_inv_pristine : ctx->d_inv_live;
+    a.inv_dst = ctx->d_inv_live;
+    a.node_off = ctx->d_node_off;
+    a.tbl = ctx->d_tbl;
+    a.out = d_out; a.n_out = n_out; a.n_node = n_node; a.have_off = d_out_off != nullptr;
+    a.err = err;
+
+    // Small batches: ONE launch.  Every node's CTA filters the claim stream for itself (n_node * n_claim key
+    // tests spread over n_node SMs, data from L2) and packs — no sort, no sorted copy.
+    constexpr int FUSED_NW = 8;
+    const size_t fused_smem = fused_smem_bytes(n_claim, FUSED_NW);
+    const bool fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) &&
+                       (uint64_t)n_node * n_claim <= ctx->fused_max_work && fused_smem <= 220 * 1024 && n_node <= 16384;
+    if (fused) {
+        if (fused_smem > 48 * 1024 && ctx->fused_smem_set < (int)fused_smem) {
+            CU(cudaFuncSetAttribute(k_fused<FUSED_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            ctx->fused_smem_set = (int)fused_smem;
+        }
+        a.claims = d_claims; a.out_off = d_out_off; a.n_claim = n_claim;
+        prof.mark(); prof.mark(); prof.mark();
+        k_fused<FUSED_NW><<<std::max(n_node, 1u), FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
+        ctx->launches += 1;
+        prof.mark();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+        return DRA_OK;
+    }
+
     if (flags & DRA_F_NODE_SORTED) {
         uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
         k_sorted_prep<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
@@ -213,36 +244,48 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         ctx->launches += 1;
         prof.mark(); prof.mark(); prof.mark();
     } else {
-        Tiling t = tiling(n_claim);
-        size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
-        if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
-        if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
-            CU(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctx->hist_smem_set = (int)smem;
+        const size_t nbp = ((size_t)n_node + 2) & ~(size_t)1;
+        const size_t small_smem = nbp * 4 + 32 * nbp * 2 + (size_t)n_claim * 2 + 16;
+        if (n_claim <= 8192 && small_smem <= 200 * 1024) {
+            // one launch: the whole stable counting sort in a single CTA
+            if (small_smem > 48 * 1024 && ctx->small_smem_set < (int)small_smem) {
+                CU(cudaFuncSetAttribute(k_bucket_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+                ctx->small_smem_set = (int)small_smem;
+            }
+            Prefetch pf;
+            pf.p[0] = a.inv_src;
+            pf.bytes[0] = std::min<uint32_t>(ctx->n_gpu * 16u, 1u << 20) & ~15u;
+            pf.p[1] = ctx->d_node_off; pf.bytes[1] = std::min<uint32_t>((n_node + 1) * 4u, 1u << 20) & ~15u;
+            pf.p[2] = ctx->d_tbl; pf.bytes[2] = 1024;
+            k_bucket_small<<<1, 1024, small_smem, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
+                                                                 ctx->d_sorted, d_out, n_out, err, pf);
+            ctx->launches += 1;
+            prof.mark(); prof.mark(); prof.mark();
+        } else {
+            Tiling t = tiling(n_claim);
+            size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
+            if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
+            if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
+                CU(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctx->hist_smem_set = (int)smem;
+            }
+            k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
+            prof.mark();
+            k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off);
+            prof.mark();
+            uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
+            k_bucket_scatter<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
+                                                              ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err);
+            prof.mark();
+            ctx->launches += 3;
         }
-        k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
-        prof.mark();
-        k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off);
-        prof.mark();
-        uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
-        k_bucket_scatter<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
-                                                          ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err);
-        prof.mark();
-        ctx->launches += 3;
     }
 
-    PackArgs a;
     a.sorted = ctx->d_sorted;
     a.claim_off = ctx->d_claim_off;
-    a.inv_src = (flags & DRA_F_FRESH_INVENTORY) ? ctx->d_inv_pristine : ctx->d_inv_live;
-    a.inv_dst = ctx->d_inv_live;
-    a.node_off = ctx->d_node_off;
-    a.tbl = ctx->d_tbl;
-    a.out = d_out; a.n_out = n_out; a.n_node = n_node; a.have_off = d_out_off != nullptr;
-    a.err = err;
     if (n_node) {
-        if (n_node <= 148u * 16u) k_pack<1><<<n_node, 32, 0, ctx->stream>>>(a);
-        else k_pack<4><<<std::min((n_node + 3) / 4, 148u * 8u), 128, 0, ctx->stream>>>(a);
+        if (n_node <= 148u * 16u) k_pack<1><<<n_node, 32, pack_smem_bytes(1), ctx->stream>>>(a);
+        else k_pack<4><<<std::min((n_node + 3) / 4, 148u * 8u), 128, pack_smem_bytes(4), ctx->stream>>>(a);
         ctx->launches += 1;
     }
     prof.mark();

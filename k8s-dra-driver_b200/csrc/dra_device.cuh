@@ -74,8 +74,26 @@ __device__ __forceinline__ void tma_load_1d(void* sdst, const void* gsrc, uint32
         ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2(const void* g, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+}
+
+
+// Lanes whose key equals mine, as a mask — __match_any_sync semantics built from one ballot per key bit.
+// MATCH.ANY serialises over the distinct values in the warp (~29 of 32 for node keys) on a unit shared by
+// the SM; log2(n_node) VOTEs pipeline.  Inactive lanes must pass act=false (their result is unused).
+__device__ __forceinline__ uint32_t peers_by_bits(uint32_t key, uint32_t nbits, bool act) {
+    uint32_t peers = __ballot_sync(FULLMASK, act);
+    for (uint32_t b = 0; b < nbits; ++b) {
+        const bool bit = (key >> b) & 1u;
+        const uint32_t m = __ballot_sync(FULLMASK, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
 }
 
 // bit i of the result: slices i .. i+size-1 of `free16` are all free (log-step AND of shifted copies)
@@ -296,6 +314,7 @@ k_bucket_hist(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_nod
               uint32_t* __restrict__ hist, uint16_t* __restrict__ rank) {
     extern __shared__ uint16_t cnt[];
     const uint32_t lane = threadIdx.x, nb = n_node + 1;
+    const uint32_t nbits = 32u - (uint32_t)__clz(n_node);          // keys are 0..n_node
     for (uint32_t n = lane; n < nb; n += 32) cnt[n] = 0;
     __syncwarp();
     const uint32_t base = blockIdx.x * T;
@@ -305,7 +324,7 @@ k_bucket_hist(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_nod
         const bool act = i < end;
         uint32_t key = 0xFFFFFFFFu;
         if (act) { key = __ldg(&claims[i]).y; key = key < n_node ? key : n_node; }
-        const uint32_t m = __match_any_sync(FULLMASK, key);
+        const uint32_t m = peers_by_bits(key, nbits, act);
         const uint32_t r = (uint32_t)__popc(m & lanemask_lt());
         uint32_t old = 0;
         if (act) { old = cnt[key]; rank[i] = (uint16_t)(old + r); }
@@ -390,6 +409,136 @@ k_bucket_scatter(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_
     sorted[dest] = c;
 }
 
+// What later kernels of the batch will read: pulled into L2 by the first kernel so that the pack kernel's
+// dependent round trips are L2 hits, not DRAM misses (cp.async.bulk.prefetch.L2).
+struct Prefetch { const void* p[3]; uint32_t bytes[3]; };
+
+// Whole stable counting sort in ONE CTA of 1024 threads, for batches that fit (n_claim <= 32768 and
+// 32*(n_node+1) u16 counters + n_claim u16 ranks in shared memory).  Replaces hist+scan+scatter by one launch:
+//   warp w owns claims [w*R*32, (w+1)*R*32) (R rows of 32);  per-warp counters keep the pass stable.
+// Loads are issued 16 rows at a time before any of them is used (cold-DRAM latency paid once per chunk).
+// Dynamic smem layout: u32 off[nb] | u16 cnt[32][nb] | u16 rank[n_claim]
+constexpr int BS_CHUNK = 16;
+__global__ void __launch_bounds__(1024)
+k_bucket_small(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
+               const uint32_t* __restrict__ out_off, uint32_t* __restrict__ claim_off,
+               uint4* __restrict__ sorted, uint2* __restrict__ out, uint32_t n_out, Err err, Prefetch pf) {
+    extern __shared__ uint32_t sm_u32[];
+    const uint32_t nb = n_node + 1, nbp = (nb + 1) & ~1u;
+    uint32_t* off = sm_u32;                                        // [nbp]
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(off + nbp);        // [32][nbp]
+    uint16_t* rnk = cnt + 32 * nbp;                                // [n_claim]
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s, total_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0 && pf.bytes[0]) tma_prefetch_l2(pf.p[0], pf.bytes[0]);
+    if (tid == 32 && pf.bytes[1]) tma_prefetch_l2(pf.p[1], pf.bytes[1]);
+    if (tid == 64 && pf.bytes[2]) tma_prefetch_l2(pf.p[2], pf.bytes[2]);
+
+    const uint32_t R = (n_claim + 1023) / 1024;                    // rows per warp
+    const uint32_t w0 = wid * R * 32;
+    uint16_t* mycnt = cnt + wid * nbp;
+    const uint32_t nbits = 32u - (uint32_t)__clz(n_node);          // keys are 0..n_node
+
+    // first chunk of keys in flight while the counters are cleared
+    uint32_t keys[BS_CHUNK];
+    #pragma unroll
+    for (int q = 0; q < BS_CHUNK; ++q) {
+        const uint32_t i = w0 + q * 32 + lane;
+        keys[q] = ((uint32_t)q < R && i < n_claim) ? __ldg(&claims[i]).y : 0xFFFFFFFFu;
+    }
+    for (uint32_t i = tid; i < 16 * nbp; i += 1024) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+
+    for (uint32_t r0 = 0; r0 < R; r0 += BS_CHUNK) {
+        if (r0) {
+            #pragma unroll
+            for (int q = 0; q < BS_CHUNK; ++q) {
+                const uint32_t i = w0 + (r0 + q) * 32 + lane;
+                keys[q] = (r0 + q < R && i < n_claim) ? __ldg(&claims[i]).y : 0xFFFFFFFFu;
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < BS_CHUNK; ++q) {
+            if (r0 + q < R) {                                       // warp-uniform
+                const uint32_t i = w0 + (r0 + q) * 32 + lane;
+                const bool act = i < n_claim;
+                const uint32_t key = act ? (keys[q] < n_node ? keys[q] : n_node) : 0xFFFFFFFFu;
+                const uint32_t m = peers_by_bits(key, nbits, act);
+                const uint32_t rk = (uint32_t)__popc(m & lanemask_lt());
+                uint32_t old = 0;
+                if (act) { old = mycnt[key]; rnk[i] = (uint16_t)(old + rk); }
+                __syncwarp();
+                if (act && rk == 0) mycnt[key] = (uint16_t)(old + (uint32_t)__popc(m));
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+
+    // per node: exclusive scan over the 32 warps' counters, then block scan of node totals
+    for (uint32_t n0 = 0; n0 < nb; n0 += 1024) {
+        const uint32_t n = n0 + tid;
+        uint32_t run = 0;
+        if (n < nb) {
+            #pragma unroll 8
+            for (uint32_t w = 0; w < 32; ++w) { const uint32_t v = cnt[w * nbp + n]; cnt[w * nbp + n] = (uint16_t)run; run += v; }
+        }
+        uint32_t x = run;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, x, d); if (lane >= (uint32_t)d) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t w = wsum[lane];
+            uint32_t ws = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, ws, d); if (lane >= (uint32_t)d) ws += y; }
+            wsum[lane] = ws - w;
+            if (lane == 31) total_s = ws;
+        }
+        __syncthreads();
+        const uint32_t excl = carry_s + wsum[wid] + (x - run);
+        if (n < nb) { off[n] = excl; claim_off[n] = excl; }
+        __syncthreads();
+        if (tid == 0) carry_s += total_s;
+        __syncthreads();
+    }
+    if (tid == 0) claim_off[nb] = carry_s;
+
+    // scatter: claims come back from L2 now; again all loads of a chunk before the first use
+    for (uint32_t r0 = 0; r0 < R; r0 += BS_CHUNK / 2) {
+        uint4 cc[BS_CHUNK / 2]; uint32_t dd[BS_CHUNK / 2];
+        #pragma unroll
+        for (int q = 0; q < BS_CHUNK / 2; ++q) {
+            const uint32_t i = w0 + (r0 + q) * 32 + lane;
+            const bool act = r0 + q < R && i < n_claim;
+            cc[q] = act ? __ldg(&claims[i]) : make_uint4(0, 0, 0, 0);
+            dd[q] = act ? (out_off ? __ldg(&out_off[i]) : i) : 0;
+        }
+        #pragma unroll
+        for (int q = 0; q < BS_CHUNK / 2; ++q) {
+            const uint32_t i = w0 + (r0 + q) * 32 + lane;
+            if (r0 + q >= R || i >= n_claim) continue;
+            uint4 c = cc[q];
+            const uint32_t dst = dd[q];
+            if (c.y >= n_node) {
+                const uint32_t kind = c.x & 0xFFu;
+                const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU
+                                  : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
+                if (dst < n_out) out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+                else err.set(ERR_OUT_RANGE);
+                continue;
+            }
+            const uint32_t dest = off[c.y] + mycnt[c.y] + rnk[i];
+            c.y = dst;
+            sorted[dest] = c;
+        }
+    }
+}
+
 // DRA_F_NODE_SORTED input: verify order, build claim_off by boundary detection, copy with slot embedded.
 __global__ void __launch_bounds__(256)
 k_sorted_prep(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
@@ -424,8 +573,11 @@ k_sorted_prep(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_nod
 // ====================================================================================================
 
 struct PackArgs {
-    const uint4* sorted;          // node-sorted claims, .y = first out slot
-    const uint32_t* claim_off;    // [n_node+2]
+    const uint4* sorted;          // node-sorted claims, .y = first out slot          (k_pack)
+    const uint32_t* claim_off;    // [n_node+2]                                        (k_pack)
+    const uint4* claims;          // claims in input order                             (k_fused)
+    const uint32_t* out_off;      // first out slot per claim or NULL                  (k_fused)
+    uint32_t n_claim;             //                                                   (k_fused)
     const uint4* inv_src;         // inventory read from here ...
     uint4* inv_dst;               // ... and written back here (may alias inv_src)
     const uint32_t* node_off;     // [n_node+1]
@@ -435,93 +587,430 @@ struct PackArgs {
     Err err;
 };
 
-struct __align__(16) WarpSmem {
-    uint4 inv[DRA_MAX_GPUS_PER_NODE];          // 512 B  node's GpuRecs
-    uint4 ring[RING][SEG];                     // 2 KiB  claim segments
-    uint64_t bar[RING + 1];                    // ring slot barriers + inventory barrier
-    uint64_t pad;
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_init_a(uint32_t addr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared (shared-space addresses), completion on an mbarrier
+__device__ __forceinline__ void tma_load_a(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+// shared-space base of the dynamic shared memory, made opaque so that it lives in a register instead of
+// being rematerialised from SR_CgaCtaId at every use
+__device__ __forceinline__ uint32_t smem_base(const void* dyn) {
+    uint32_t b = smem_u32(dyn);
+    asm volatile("" : "+r"(b));
+    return b;
+}
+
+// shift schedule of fit_map for a given size, 4 nibbles: t &= t >> s_i, i = 0..3 (covers sizes 1..16)
+__device__ __forceinline__ uint32_t shifts_of(uint32_t size) {
+    uint32_t c = 1, sh = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) { const uint32_t s_ = min(c, size - c) & 15u; sh |= s_ << (4 * i); c += s_; }
+    return sh;
+}
+
+// The warp that packs one node: one lane per GPU.
+struct NodeCtx {
+    Lane L; Dead D; OutSink sink;
+    uint32_t lane, ltmask, g0, m0, k_next;
+    uint32_t live_addr;            // shared: 32 prepared records x 32 B
+    uint32_t tbl_addr;             // shared: placement table (u32 cells)
+    const uint32_t* tbl_ptr;       // same table for the generic step
+    bool homog, mig_ok, mig_offer, have_off;
+
+    __device__ __forceinline__ void begin(uint4 rec, bool valid) {
+        constexpr uint32_t BLOCKED = DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE;
+        L.load(rec, valid);
+        D = Dead();
+        k_next = 0;
+        // facts that cannot change during the batch (FULL is only ever set on non-MIG GPUs)
+        mig_offer = L.valid && (L.flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_UNAVAILABLE)) == DRA_GPU_MIG_ENABLED;
+        mig_ok = L.valid && (L.flags & BLOCKED) == DRA_GPU_MIG_ENABLED;
+        m0 = __shfl_sync(FULLMASK, L.model, 0);
+        homog = __all_sync(FULLMASK, !L.valid || L.model == m0);     // one placement-table row for the node
+    }
 };
+
+// One segment of <= 32 consecutive claims of the node; lane j holds claim j (c.y = first out slot).
+//   1. lane-parallel: malformed claims and request shapes already known to fail on this node (Dead memo)
+//      write their own OutRec, 32 at a time; live claims are compacted, in order, into prepared records;
+//   2. serial: the live records, in order — candidate starts by a log-step shift/AND on the lane's occupancy
+//      mask, __ballot_sync + __ffs = lowest GPU, __ffs of the winner's candidates = lowest start.
+template <class Get>
+__device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const bool present, const uint32_t pos,
+                                            Get get, const uint32_t cnt) {
+    constexpr uint32_t BLOCKED = DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE;
+    Lane& L = x.L; Dead& D = x.D; OutSink& sink = x.sink;
+    const uint32_t lane = x.lane, g0 = x.g0;
+    const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
+    const uint32_t dst = c.y, mem = c.z, group = c.w;
+    bool live = present && pos >= x.k_next;
+    const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : prof;
+    if (live && claim_invalid(kind, prof, count, x.have_off)) {            // spec §3
+        if (dst < sink.n_out) sink.put(dst, DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+        else sink.err.set(ERR_OUT_RANGE);
+        live = false;
+    }
+    const uint32_t slots = kind == DRA_KIND_GPU ? count : 1u;
+    const bool is_group = kind == DRA_KIND_MIG && group != 0;
+    if (live && !is_group && (dst > sink.n_out || slots > sink.n_out - dst)) { sink.err.set(ERR_OUT_RANGE); live = false; }
+    if (live && !is_group) {                                               // shapes that already failed here
+        bool dead = false; uint32_t st = DRA_ST_NO_CAPACITY;
+        if (kind == DRA_KIND_MIG) {
+            const uint32_t pbit = 1u << prof;
+            if (D.bad & pbit) { dead = true; st = DRA_ST_BAD_PROFILE; } else if (D.nocap & pbit) dead = true;
+        } else if (kind == DRA_KIND_GPU) dead = count >= D.gpu_min;
+        else { dead = (uint64_t)mem >= D.sh_min; st = DRA_ST_MEM_LIMIT; }
+        if (dead) {
+            for (uint32_t s_ = 0; s_ < slots; ++s_) sink.put(dst + s_, DRA_GPU_NONE, meta(0, 0, op, st));
+            live = false;
+        }
+    }
+    // prepared record of a live claim (what the serial step needs, already unpacked):
+    //   r0 = {s1, s2, s3, s4}  shift schedule (MIG) | {count or mem or position, 0, 0, 0}
+    //   r1 = {smask | prof<<16 | class<<24, first out slot, OutRec meta (size<<8 | prof<<16), (1<<size)-1}
+    const uint32_t lm = __ballot_sync(FULLMASK, live);
+    if (lm == 0) return;
+    if (live) {
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, dst, 0, 0);
+        if (is_group) { r0.x = pos; r1.x = 4u << 24; }
+        else if (kind == DRA_KIND_MIG) {
+            const uint32_t e = lds32(x.tbl_addr + ((x.m0 * DRA_MAX_PROFILES + prof) << 2));   // homogeneous node: one cell for all GPUs
+            const uint32_t size = e & 0xFFu, sh = shifts_of(size);
+            r0 = make_uint4(sh & 15u, (sh >> 4) & 15u, (sh >> 8) & 15u, sh >> 12);
+            r1.x = (e >> 16) | (prof << 16) | (1u << 24);
+            r1.z = (size << 8) | (prof << 16);
+            r1.w = (1u << size) - 1u;
+        } else if (kind == DRA_KIND_GPU) { r0.x = count; r1.x = 2u << 24; }
+        else { r0.x = mem; r1.x = 3u << 24; }
+        const uint32_t at = x.live_addr + ((uint32_t)__popc(lm & x.ltmask) << 5);
+        sts128(at, r0); sts128(at + 16, r1);
+    }
+    __syncwarp();
+    const uint32_t nlive = (uint32_t)__popc(lm);
+
+    uint4 n0 = lds128(x.live_addr), n1 = lds128(x.live_addr + 16);
+    for (uint32_t q = 0; q < nlive; ++q) {
+        const uint4 r0 = n0, r1 = n1;
+        if (q + 1 < nlive) { n0 = lds128(x.live_addr + ((q + 1) << 5)); n1 = lds128(x.live_addr + ((q + 1) << 5) + 16); }
+        const uint32_t cls = r1.x >> 24, dj = r1.y;
+        if (cls == 1u) {                                   // MIG, spec §5
+            const uint32_t pj = (r1.x >> 16) & 0xFFu;
+            if (((D.bad | D.nocap) >> pj) & 1u) {          // shape died earlier in this segment
+                if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, pj, ((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY));
+                continue;
+            }
+            uint32_t smask = r1.x & 0xFFFFu, s1 = r0.x, s2 = r0.y, s3 = r0.z, s4 = r0.w, mm = r1.z, sbits = r1.w;
+            if (!x.homog) {                                // per-GPU table row
+                const uint32_t e = lds32(x.tbl_addr + ((L.model * DRA_MAX_PROFILES + pj) << 2));
+                const uint32_t size = e & 0xFFu, sh = shifts_of(size);
+                smask = e >> 16; s1 = sh & 15u; s2 = (sh >> 4) & 15u; s3 = (sh >> 8) & 15u; s4 = sh >> 12;
+                mm = (size << 8) | (pj << 16); sbits = (1u << size) - 1u;
+            }
+            uint32_t t = ~L.busy & 0xFFFFu;
+            t &= t >> s1; t &= t >> s2; t &= t >> s3; t &= t >> s4;
+            const uint32_t cand = x.mig_ok ? (t & smask) : 0u;
+            const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
+            const uint32_t st = (uint32_t)__ffs(cand) - 1u;              // lowest start (if this lane wins)
+            const bool win = lane == (uint32_t)__ffs(b) - 1u;            // lowest GPU; b == 0: nobody
+            if (win) { L.busy |= sbits << (st & 31u); sink.put(dj, g0 + lane, mm | st); }
+            if (b == 0) {
+                const bool any = __ballot_sync(FULLMASK, x.mig_offer && smask != 0) != 0;
+                if (any) D.nocap |= 1u << pj; else D.bad |= 1u << pj;
+                if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, pj, any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE));
+            }
+        } else if (cls == 2u) {                            // full GPUs, spec §4
+            const uint32_t cj = r0.x;
+            if (cj >= D.gpu_min) { if (lane < cj) sink.put(dj + lane, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY)); continue; }
+            const bool elig = L.valid && !(L.flags & BLOCKED) && L.share == 0;
+            const uint32_t b = __ballot_sync(FULLMASK, elig);
+            const uint32_t r = (uint32_t)__popc(b & x.ltmask);
+            if ((uint32_t)__popc(b) >= cj) {
+                if (elig && r < cj) { L.flags |= DRA_GPU_FULL_ALLOCATED; sink.put(dj + r, g0 + lane, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_OK)); }
+            } else {
+                D.gpu_min = cj;
+                if (lane < cj) sink.put(dj + lane, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY));
+            }
+        } else if (cls == 3u) {                            // shared GPU, spec §7
+            const uint32_t mj = r0.x;
+            if ((uint64_t)mj >= D.sh_min) { if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT)); continue; }
+            const bool elig = L.valid && !(L.flags & BLOCKED) && L.share < 0xFFFFu && L.mem >= mj;
+            const uint32_t b = __ballot_sync(FULLMASK, elig);
+            const bool win = lane == (uint32_t)__ffs(b) - 1u;
+            if (win) { L.mem -= mj; L.share += 1; sink.put(dj, g0 + lane, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_OK)); }
+            if (b == 0) {
+                D.sh_min = mj;
+                if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT));
+            }
+        } else {                                           // co-location run: generic step
+            const uint32_t pj = r0.x;
+            if (pj >= x.k_next) x.k_next = pj + node_step(L, D, lane, g0, x.tbl_ptr, get, pj, cnt, sink, x.have_off);
+        }
+    }
+    __syncwarp();
+}
+
+// ---- k_pack: node-sorted claims (output of the bucketing kernels), one warp per node -------------------
+// dynamic smem per CTA: [tbl 1024][tbar 16][per warp: inv 512 | ring 2048 | live 1024 | bars 48]
+constexpr uint32_t PK_TBL = 0, PK_TBAR = 1024, PK_WARP0 = 1040, PK_INV = 0, PK_RING = 512, PK_LIVE = 2560,
+                   PK_BARS = 3584, PK_WSTRIDE = 3632;
+__host__ __device__ constexpr uint32_t pack_smem_bytes(int wpc) { return PK_WARP0 + (uint32_t)wpc * PK_WSTRIDE; }
 
 // claim m of the node's span from the shared-memory ring (all lanes read one address: broadcast)
 struct RingGet {
-    const WarpSmem* ws; uint32_t segbase;
+    uint32_t ring_addr; uint32_t segbase;
     __device__ __forceinline__ uint4 operator()(uint32_t m) const {
-        return ws->ring[(segbase + (m >> 5)) & (RING - 1)][m & 31];
+        return lds128(ring_addr + ((((segbase + (m >> 5)) & (RING - 1)) * SEG + (m & 31)) << 4));
     }
 };
 
+// Every load that does not depend on another is issued before the first wait: the bench flushes L2, so each
+// dependent round trip is a DRAM (or at best L2) latency.
 template <int WPC>
 __global__ void __launch_bounds__(WPC * 32)
 k_pack(const PackArgs a) {
-    __shared__ uint32_t tbl_s[DRA_MAX_MODELS * DRA_MAX_PROFILES];
-    __shared__ WarpSmem wsm[WPC];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const uint32_t sbase = smem_base(dyn_smem);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSmem& ws = wsm[wid];
+    const uint32_t wbase = sbase + PK_WARP0 + wid * PK_WSTRIDE;
+    const uint32_t ring_addr = wbase + PK_RING, bar_addr = wbase + PK_BARS, inv_addr = wbase + PK_INV;
+    const uint32_t tbar_addr = sbase + PK_TBAR;
 
-    for (uint32_t i = threadIdx.x; i < DRA_MAX_MODELS * DRA_MAX_PROFILES; i += WPC * 32) tbl_s[i] = __ldg(&a.tbl[i]);
     if (lane == 0) {
         #pragma unroll
-        for (int q = 0; q <= (int)RING; ++q) mbar_init(&ws.bar[q], 1);
+        for (int q = 0; q <= (int)RING; ++q) mbar_init_a(bar_addr + q * 8, 1);
+        if (wid == 0) mbar_init_a(tbar_addr, 1);
         mbar_fence_init();
     }
     __syncthreads();
+    if (threadIdx.x == 0) tma_load_a(sbase + PK_TBL, a.tbl, 1024u, tbar_addr);   // placement table, waited on later
+    bool tbl_ready = false;
 
-    if (a.err.dev[ERR_NOT_SORTED]) return;     // input contract violated upstream: leave the inventory alone
+    NodeCtx x;
+    x.lane = lane; x.ltmask = lanemask_lt();
+    x.live_addr = wbase + PK_LIVE; x.tbl_addr = sbase + PK_TBL;
+    x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + PK_TBL);
+    x.have_off = a.have_off != 0;
+    x.sink = OutSink{a.out, a.n_out, a.err, lane};
 
     uint32_t segbase = 0;      // running segment counter: ring slot = (segbase+q) % RING
     uint32_t inv_phase = 0;
     const uint32_t nwarps = gridDim.x * WPC;
     for (uint32_t node = blockIdx.x * WPC + wid; node < a.n_node; node += nwarps) {
+        // one round trip: the node's extents and the upstream error flag
         const uint32_t g0 = __ldg(&a.node_off[node]);
-        const uint32_t ng = __ldg(&a.node_off[node + 1]) - g0;
+        const uint32_t g1 = __ldg(&a.node_off[node + 1]);
         const uint32_t c0 = __ldg(&a.claim_off[node]);
-        const uint32_t cnt = __ldg(&a.claim_off[node + 1]) - c0;
+        const uint32_t c1 = __ldg(&a.claim_off[node + 1]);
+        const uint32_t bad_input = a.err.dev[ERR_NOT_SORTED];
+        const uint32_t ng = g1 - g0, cnt = c1 - c0;
+        if (bad_input) return;                  // input contract violated upstream: leave the inventory alone
         if (cnt == 0) {
             if (a.inv_src != a.inv_dst && lane < ng) a.inv_dst[g0 + lane] = __ldg(&a.inv_src[g0 + lane]);
             continue;
         }
         const uint32_t nseg = (cnt + SEG - 1) / SEG;
-        uint32_t issued = 0, waited = 0;
-
+        uint32_t issued = 0;
         auto issue = [&](uint32_t q) {
             if (lane == 0) {
-                const uint32_t n = min(SEG, cnt - q * SEG) * 16u;
-                uint64_t* bar = &ws.bar[(segbase + q) & (RING - 1)];
-                mbar_arrive_expect_tx(bar, n);
-                tma_load_1d(&ws.ring[(segbase + q) & (RING - 1)][0], a.sorted + c0 + q * SEG, n, bar);
+                const uint32_t slot = (segbase + q) & (RING - 1);
+                tma_load_a(ring_addr + slot * SEG * 16, a.sorted + c0 + q * SEG, min(SEG, cnt - q * SEG) * 16u, bar_addr + slot * 8);
             }
         };
-        // stage the node: GpuRecs + first claim segments, all in flight at once
-        if (lane == 0 && ng) {
-            mbar_arrive_expect_tx(&ws.bar[RING], ng * 16u);
-            tma_load_1d(&ws.inv[0], a.inv_src + g0, ng * 16u, &ws.bar[RING]);
-        }
+        // second round trip: GpuRecs + first claim segments, all in flight at once
+        if (lane == 0 && ng) tma_load_a(inv_addr, a.inv_src + g0, ng * 16u, bar_addr + RING * 8);
         while (issued < nseg && issued < 3) issue(issued++);
+        if (!tbl_ready) { mbar_wait_a(tbar_addr, 0); tbl_ready = true; }
 
         uint4 rec = make_uint4(0, 0, 0, 0);
-        if (ng) { mbar_wait(&ws.bar[RING], inv_phase); inv_phase ^= 1; if (lane < ng) rec = ws.inv[lane]; }
-        Lane L; L.load(rec, lane < ng);
-        Dead D;
-        OutSink sink{a.out, a.n_out, a.err, lane};
-        RingGet get{&ws, segbase};
+        if (ng) { mbar_wait_a(bar_addr + RING * 8, inv_phase); inv_phase ^= 1; if (lane < ng) rec = lds128(inv_addr + lane * 16); }
+        x.g0 = g0;
+        x.begin(rec, lane < ng);
+        RingGet get{ring_addr, segbase};
 
-        uint32_t k = 0;
-        while (k < cnt) {
-            const uint32_t seg = k >> 5;
-            const uint32_t need = min(nseg - 1, seg + 1);       // current + look-ahead for runs
+        uint32_t waited = 0;
+        for (uint32_t seg = 0; seg < nseg; ++seg) {
+            const uint32_t need = min(nseg - 1, seg + 1);           // current + look-ahead for runs
             while (waited <= need) {
-                mbar_wait(&ws.bar[(segbase + waited) & (RING - 1)], ((segbase + waited) / RING) & 1);
+                mbar_wait_a(bar_addr + ((segbase + waited) & (RING - 1)) * 8, ((segbase + waited) / RING) & 1);
                 ++waited;
             }
-            // slots of seg and seg+1 are live; seg+2 may be in flight; seg-1's slot is free
             __syncwarp();
-            while (issued < nseg && issued <= seg + 2) issue(issued++);
-            k += node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, a.have_off != 0);
+            while (issued < nseg && issued <= seg + 2) issue(issued++);   // slot of seg-1 is free by now
+            const uint32_t n_in = min(SEG, cnt - seg * SEG);
+            const uint32_t slot = (segbase + seg) & (RING - 1);
+            uint4 c = make_uint4(0xFFu, 0, 0, 0);
+            if (lane < n_in) c = lds128(ring_addr + ((slot * SEG + lane) << 4));
+            segment_run(x, c, lane < n_in, seg * SEG + lane, get, cnt);
         }
-        if (lane < ng) a.inv_dst[g0 + lane] = L.store(rec);
+        if (lane < ng) a.inv_dst[g0 + lane] = x.L.store(rec);
         segbase += nseg;
         __syncwarp();
     }
+}
+
+// ---- k_fused: the whole Allocate batch in ONE launch, for batches where n_node * n_claim is small --------
+// One CTA of NW warps per node.  All warps stream the claim array (each its own contiguous part, so every
+// warp's matches are in input order) and keep the indices of the claims that select this node; then warp 0
+// packs them.  No sort, no sorted copy, no claim_off: the O(n_node * n_claim) key tests are spread over
+// n_node SMs and every byte after the first CTA's touch comes from L2.
+// dynamic smem: [tbl 1024][bars 16][inv 512][live 1024][counts 64][index lists: n_claim u32, warp w at w*chunk]
+constexpr uint32_t FU_TBL = 0, FU_TBAR = 1024, FU_IBAR = 1032, FU_INV = 1040, FU_LIVE = 1552, FU_CNT = 2576, FU_LIST = 2640;
+__host__ __device__ constexpr size_t fused_smem_bytes(uint32_t n_claim, int nw) {
+    return FU_LIST + ((size_t)((n_claim + nw * 32 - 1) / (nw * 32)) * 32 * nw) * 4 + 16;
+}
+
+template <int NW>
+struct IdxGet {            // claim m of the node from the index lists (generic / co-location path only)
+    const uint4* claims; const uint32_t* out_off; uint32_t list_addr, chunk; uint32_t pre[NW];
+    __device__ __forceinline__ uint32_t index_of(uint32_t m) const {
+        uint32_t w = 0;
+        #pragma unroll
+        for (int i = 1; i < NW; ++i) w += m >= pre[i];
+        uint32_t base = 0;
+        #pragma unroll
+        for (int i = 1; i < NW; ++i) base = (w == (uint32_t)i) ? pre[i] : base;
+        return lds32(list_addr + ((w * chunk + (m - base)) << 2));
+    }
+    __device__ __forceinline__ uint4 operator()(uint32_t m) const {
+        const uint32_t i = index_of(m);
+        uint4 c = __ldg(&claims[i]);
+        c.y = out_off ? __ldg(&out_off[i]) : i;
+        return c;
+    }
+};
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_fused(const PackArgs a) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const uint32_t sbase = smem_base(dyn_smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t node = blockIdx.x;
+    const bool has_node = node < a.n_node;
+    const uint32_t tbar = sbase + FU_TBAR, ibar = sbase + FU_IBAR, list_addr = sbase + FU_LIST;
+
+    // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
+    uint32_t g0 = 0, g1 = 0;
+    if (has_node) { g0 = __ldg(&a.node_off[node]); g1 = __ldg(&a.node_off[node + 1]); }
+    if (threadIdx.x == 0) {
+        mbar_init_a(tbar, 1); mbar_init_a(ibar, 1);
+        mbar_fence_init();
+        tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
+    }
+    const uint32_t ng = g1 - g0;
+    if (threadIdx.x == 0 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
+
+    // ---- filter: which claims select this node (all warps) ------------------------------------------
+    const uint32_t chunk = ((a.n_claim + NW * 32 - 1) / (NW * 32)) * 32;      // per-warp part, multiple of 32
+    const uint32_t lo = wid * chunk, hi = min(a.n_claim, lo + chunk);
+    const uint32_t ltmask = lanemask_lt();
+    const uint32_t my_list = list_addr + (lo << 2);
+    const uint32_t want = has_node ? node : 0xFFFFFFFEu;
+    uint32_t cntw = 0;
+    constexpr int U = 8;
+    for (uint32_t base = lo; base < hi; base += 32 * U) {
+        uint32_t key[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = base + u * 32 + lane;
+            key[u] = i < hi ? __ldg(reinterpret_cast<const uint32_t*>(a.claims + i) + 1) : 0xFFFFFFFFu;
+        }
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = base + u * 32 + lane;
+            const bool m = key[u] == want;
+            const uint32_t b = __ballot_sync(FULLMASK, m);
+            if (b) {
+                if (m) sts32(my_list + ((cntw + (uint32_t)__popc(b & ltmask)) << 2), i);
+                cntw += (uint32_t)__popc(b);
+            }
+            if (node == 0) {                       // claims that name no node: INVALID, written by CTA 0 (spec §3)
+                const bool none = i < hi && key[u] >= a.n_node;
+                if (__any_sync(FULLMASK, none) && none) {
+                    const uint4 c = __ldg(&a.claims[i]);
+                    const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
+                    const uint32_t kind = c.x & 0xFFu;
+                    const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
+                    if (dst < a.n_out) a.out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+                    else a.err.set(ERR_OUT_RANGE);
+                }
+            }
+        }
+    }
+    if (lane == 0) sts32(sbase + FU_CNT + (wid << 2), cntw);
+    __syncthreads();
+    if (wid != 0 || !has_node) return;
+
+    // ---- pack: warp 0 ----------------------------------------------------------------------------------
+    IdxGet<NW> get;
+    get.claims = a.claims; get.out_off = a.out_off; get.list_addr = list_addr; get.chunk = chunk;
+    uint32_t cnt = 0;
+    #pragma unroll
+    for (int i = 0; i < NW; ++i) { get.pre[i] = cnt; cnt += lds32(sbase + FU_CNT + (i << 2)); }
+    if (cnt == 0) {
+        if (a.inv_src != a.inv_dst && lane < ng) a.inv_dst[g0 + lane] = __ldg(&a.inv_src[g0 + lane]);
+        return;
+    }
+    // the first segment's claims are requested before waiting for the table / inventory
+    auto fetch = [&](uint32_t seg, uint4& c, bool& present) {
+        const uint32_t m = seg * SEG + lane;
+        present = m < cnt;
+        c = make_uint4(0xFFu, 0, 0, 0);
+        if (present) c = get(m);
+    };
+    uint4 c_cur; bool p_cur;
+    fetch(0, c_cur, p_cur);
+
+    NodeCtx x;
+    x.lane = lane; x.ltmask = ltmask;
+    x.live_addr = sbase + FU_LIVE; x.tbl_addr = sbase + FU_TBL;
+    x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + FU_TBL);
+    x.have_off = a.have_off != 0;
+    x.sink = OutSink{a.out, a.n_out, a.err, lane};
+    x.g0 = g0;
+    mbar_wait_a(tbar, 0);
+    uint4 rec = make_uint4(0, 0, 0, 0);
+    if (ng) { mbar_wait_a(ibar, 0); if (lane < ng) rec = lds128(sbase + FU_INV + lane * 16); }
+    x.begin(rec, lane < ng);
+
+    const uint32_t nseg = (cnt + SEG - 1) / SEG;
+    for (uint32_t seg = 0; seg < nseg; ++seg) {
+        uint4 c_nxt = make_uint4(0xFFu, 0, 0, 0); bool p_nxt = false;
+        if (seg + 1 < nseg) fetch(seg + 1, c_nxt, p_nxt);       // in flight while this segment is packed
+        segment_run(x, c_cur, p_cur, seg * SEG + lane, get, cnt);
+        c_cur = c_nxt; p_cur = p_nxt;
+    }
+    if (lane < ng) a.inv_dst[g0 + lane] = x.L.store(rec);
 }
 
 // ====================================================================================================

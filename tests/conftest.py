@@ -39,9 +39,12 @@ GOLDEN_CASES = ["gpu_test4", "cfg1", "cfg2_small", "cfg4_small", "cfg5_small", "
                 "mixed3", "mixed11_valid"]
 
 
-@pytest.fixture(scope="session")
-def ctx(pkg):
-    """One CUDA context for the GPU tests (fails loudly when the library or the device is missing)."""
-    c = pkg.api.Context(device=0)
+@pytest.fixture(scope="session", params=["auto", "bucket+pack"])
+def ctx(pkg, request):
+    """One CUDA context per kernel path for the GPU tests (fails loudly when the library or the device is
+    missing): "auto" takes the single-launch fused kernel whenever the batch is small enough,
+    "bucket+pack" forces the stable counting sort + pack chain."""
+    c = pkg.api.Context(device=0, flags=0 if request.param == "auto" else pkg.api.CFG_NO_FUSED)
+    c.path = request.param
     yield c
     c.close()

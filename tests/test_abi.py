@@ -69,13 +69,13 @@ def test_product_does_not_touch_the_oracle():
 
 
 def test_kernels_are_sm100a_and_use_tma(pkg):
-    """cuobjdump evidence: the cubin is sm_100a, TMA bulk copies (UBLKCP), ballots (VOTE), MATCH are in SASS."""
+    """cuobjdump evidence: the cubin is sm_100a; TMA bulk copies (UBLKCP), mbarriers (SYNCS), ballots (VOTE) in SASS."""
     so = pkg.api.SO_PATH
     r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in r.stdout
-    for mnem in ("UBLKCP", "VOTE", "MATCH.ANY", "SYNCS"):
+    for mnem in ("UBLKCP", "VOTE", "SYNCS", "LDG.E.128", "STG.E.64"):
         assert mnem in r.stdout, mnem
 
 

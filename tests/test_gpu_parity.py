@@ -203,8 +203,13 @@ def test_launch_counter_counts_our_kernels(pkg, ctx):
     ctx.set_table(w.table); ctx.set_inventory(w.gpus, w.node_off)
     before = ctx.launch_count()
     ctx.allocate(w.claims)
-    assert ctx.launch_count() - before == 4          # hist, scan, scatter, pack
+    assert ctx.launch_count() - before == (1 if ctx.path == "auto" else 2)   # fused | bucket_small, pack
     ctx.set_inventory(w.gpus, w.node_off)
     before = ctx.launch_count()
     ctx.allocate(w.node_sorted().claims, flags=pkg.api.F_NODE_SORTED)
     assert ctx.launch_count() - before == 2          # sorted_prep, pack
+    w = pkg.synth.cfg2(40_000, 300)
+    ctx.set_inventory(w.gpus, w.node_off)
+    before = ctx.launch_count()
+    ctx.allocate(w.claims)
+    assert ctx.launch_count() - before == 4          # hist, scan, scatter, pack
