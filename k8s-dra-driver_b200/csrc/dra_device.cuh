@@ -642,6 +642,7 @@ __device__ __forceinline__ uint32_t shifts_of(uint32_t size) {
 struct NodeCtx {
     Lane L; Dead D; OutSink sink;
     uint32_t lane, ltmask, g0, m0, k_next;
+    uint32_t gate;                 // 0xFFFF on lanes whose GPU can take MIG devices at all, else 0
     uint32_t live_addr;            // shared: 32 prepared records x 32 B
     uint32_t tbl_addr;             // shared: placement table (u32 cells)
     const uint32_t* tbl_ptr;       // same table for the generic step
@@ -655,6 +656,7 @@ struct NodeCtx {
         // facts that cannot change during the batch (FULL is only ever set on non-MIG GPUs)
         mig_offer = L.valid && (L.flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_UNAVAILABLE)) == DRA_GPU_MIG_ENABLED;
         mig_ok = L.valid && (L.flags & BLOCKED) == DRA_GPU_MIG_ENABLED;
+        gate = mig_ok ? 0xFFFFu : 0u;
         m0 = __shfl_sync(FULLMASK, L.model, 0);
         homog = __all_sync(FULLMASK, !L.valid || L.model == m0);     // one placement-table row for the node
     }
@@ -718,16 +720,14 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     __syncwarp();
     const uint32_t nlive = (uint32_t)__popc(lm);
 
-    uint4 n0 = lds128(x.live_addr), n1 = lds128(x.live_addr + 16);
-    for (uint32_t q = 0; q < nlive; ++q) {
-        const uint4 r0 = n0, r1 = n1;
-        if (q + 1 < nlive) { n0 = lds128(x.live_addr + ((q + 1) << 5)); n1 = lds128(x.live_addr + ((q + 1) << 5) + 16); }
+    // one live record; returns nothing, mutates L / D.  Success path of every class is branch-free.
+    auto step = [&](const uint4 r0, const uint4 r1) {
         const uint32_t cls = r1.x >> 24, dj = r1.y;
         if (cls == 1u) {                                   // MIG, spec §5
             const uint32_t pj = (r1.x >> 16) & 0xFFu;
             if (((D.bad | D.nocap) >> pj) & 1u) {          // shape died earlier in this segment
                 if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, pj, ((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY));
-                continue;
+                return;
             }
             uint32_t smask = r1.x & 0xFFFFu, s1 = r0.x, s2 = r0.y, s3 = r0.z, s4 = r0.w, mm = r1.z, sbits = r1.w;
             if (!x.homog) {                                // per-GPU table row
@@ -736,9 +736,9 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
                 smask = e >> 16; s1 = sh & 15u; s2 = (sh >> 4) & 15u; s3 = (sh >> 8) & 15u; s4 = sh >> 12;
                 mm = (size << 8) | (pj << 16); sbits = (1u << size) - 1u;
             }
-            uint32_t t = ~L.busy & 0xFFFFu;
+            uint32_t t = ~L.busy & x.gate;
             t &= t >> s1; t &= t >> s2; t &= t >> s3; t &= t >> s4;
-            const uint32_t cand = x.mig_ok ? (t & smask) : 0u;
+            const uint32_t cand = t & smask;
             const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
             const uint32_t st = (uint32_t)__ffs(cand) - 1u;              // lowest start (if this lane wins)
             const bool win = lane == (uint32_t)__ffs(b) - 1u;            // lowest GPU; b == 0: nobody
@@ -750,7 +750,7 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             }
         } else if (cls == 2u) {                            // full GPUs, spec §4
             const uint32_t cj = r0.x;
-            if (cj >= D.gpu_min) { if (lane < cj) sink.put(dj + lane, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY)); continue; }
+            if (cj >= D.gpu_min) { if (lane < cj) sink.put(dj + lane, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY)); return; }
             const bool elig = L.valid && !(L.flags & BLOCKED) && L.share == 0;
             const uint32_t b = __ballot_sync(FULLMASK, elig);
             const uint32_t r = (uint32_t)__popc(b & x.ltmask);
@@ -762,7 +762,7 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             }
         } else if (cls == 3u) {                            // shared GPU, spec §7
             const uint32_t mj = r0.x;
-            if ((uint64_t)mj >= D.sh_min) { if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT)); continue; }
+            if ((uint64_t)mj >= D.sh_min) { if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT)); return; }
             const bool elig = L.valid && !(L.flags & BLOCKED) && L.share < 0xFFFFu && L.mem >= mj;
             const uint32_t b = __ballot_sync(FULLMASK, elig);
             const bool win = lane == (uint32_t)__ffs(b) - 1u;
@@ -775,6 +775,16 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             const uint32_t pj = r0.x;
             if (pj >= x.k_next) x.k_next = pj + node_step(L, D, lane, g0, x.tbl_ptr, get, pj, cnt, sink, x.have_off);
         }
+    };
+    // ping-pong: the next record is in flight while the current one is stepped, no register shuffling
+    uint4 a0 = lds128(x.live_addr), a1 = lds128(x.live_addr + 16), b0, b1;
+    for (uint32_t q = 0; q < nlive; q += 2) {
+        const uint32_t nb_ = x.live_addr + ((q + 1) << 5);
+        if (q + 1 < nlive) { b0 = lds128(nb_); b1 = lds128(nb_ + 16); }
+        step(a0, a1);
+        if (q + 1 >= nlive) break;
+        if (q + 2 < nlive) { a0 = lds128(nb_ + 32); a1 = lds128(nb_ + 48); }
+        step(b0, b1);
     }
     __syncwarp();
 }
@@ -796,7 +806,7 @@ struct RingGet {
 // Every load that does not depend on another is issued before the first wait: the bench flushes L2, so each
 // dependent round trip is a DRAM (or at best L2) latency.
 template <int WPC>
-__global__ void __launch_bounds__(WPC * 32)
+__global__ void __launch_bounds__(WPC * 32, 1)
 k_pack(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const uint32_t sbase = smem_base(dyn_smem);
@@ -910,7 +920,7 @@ struct IdxGet {            // claim m of the node from the index lists (generic 
 };
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, 1)
 k_fused(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const uint32_t sbase = smem_base(dyn_smem);
@@ -938,12 +948,15 @@ k_fused(const PackArgs a) {
     const uint32_t want = has_node ? node : 0xFFFFFFFEu;
     uint32_t cntw = 0;
     constexpr int U = 8;
+    const uint32_t* keyp = reinterpret_cast<const uint32_t*>(a.claims) + 1;      // .y of claim i at keyp[4*i]
+    uint32_t key[U], nxt[U];
+    #pragma unroll
+    for (int u = 0; u < U; ++u) { const uint32_t i = lo + u * 32 + lane; key[u] = i < hi ? __ldg(keyp + 4 * (size_t)i) : 0xFFFFFFFFu; }
     for (uint32_t base = lo; base < hi; base += 32 * U) {
-        uint32_t key[U];
         #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t i = base + u * 32 + lane;
-            key[u] = i < hi ? __ldg(reinterpret_cast<const uint32_t*>(a.claims + i) + 1) : 0xFFFFFFFFu;
+        for (int u = 0; u < U; ++u) {                      // next batch goes out before this one is looked at
+            const uint32_t i = base + 32 * U + u * 32 + lane;
+            nxt[u] = i < hi ? __ldg(keyp + 4 * (size_t)i) : 0xFFFFFFFFu;
         }
         #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -966,6 +979,8 @@ k_fused(const PackArgs a) {
                 }
             }
         }
+        #pragma unroll
+        for (int u = 0; u < U; ++u) key[u] = nxt[u];
     }
     if (lane == 0) sts32(sbase + FU_CNT + (wid << 2), cntw);
     __syncthreads();
@@ -1031,7 +1046,7 @@ struct GlobalGet {
 };
 
 template <int WPC>
-__global__ void __launch_bounds__(WPC * 32)
+__global__ void __launch_bounds__(WPC * 32, 2)
 k_unsuitable(const UnsArgs a) {
     __shared__ uint32_t tbl_s[DRA_MAX_MODELS * DRA_MAX_PROFILES];
     for (uint32_t i = threadIdx.x; i < DRA_MAX_MODELS * DRA_MAX_PROFILES; i += WPC * 32) tbl_s[i] = __ldg(&a.tbl[i]);
