@@ -197,10 +197,28 @@ def run_ours(args):
     ctx = pkg.api.Context(device=local, stream=stream.cuda_stream, max_claims=n_claim)
     ctx.set_table(w.table)
     ctx.set_inventory(w.gpus, w.node_off)
+    collective = None
     if world > 1:
         uid = [pkg.api.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
+        collective = "ncclAllGather"
+        if not args.nccl:
+            # peer-memory all-gather: exchange the IPC handles of the gather buffers (host plumbing only)
+            ok = 1
+            try:
+                hs = [None] * world
+                dist.all_gather_object(hs, ctx.peer_export(n_out))
+                ctx.peer_import(hs)
+            except pkg.api.DraError as e:
+                ok = 0
+                print(f"[rank {rank}] peer all-gather unavailable, using NCCL: {e}", file=sys.stderr)
+            t_ok = torch.tensor([ok], device=dev)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok.item()) == 1:
+                collective = "peer-store all-gather (NVLink P2P stores + epoch flags, own kernels)"
+            else:
+                ctx.peer_disable()
 
     d_claims = torch.from_numpy(w.claims.view(np.uint8).copy()).to(dev)
     d_out_all = torch.zeros(world * n_out * 8, dtype=torch.uint8, device=dev)
@@ -221,9 +239,13 @@ def run_ours(args):
     # ---- parity guard: the timed path must produce the oracle's bytes --------------------------------
     from oracle import oracle as O
     step_dev(); ctx.sync()
-    got = d_out_all.cpu().numpy().view(R.OUT_DTYPE)[rank * n_out:(rank + 1) * n_out]
-    ref_out, _ = O.allocate(w.gpus, w.node_off, w.table, w.claims)
-    if got.tobytes() != ref_out.tobytes():
+    got_all = d_out_all.cpu().numpy().view(R.OUT_DTYPE)
+    ref_all = []
+    for r in range(world):                       # every rank checks the WHOLE gathered table
+        wr = w if r == rank else workload(pkg, r, world)
+        ref_all.append(O.allocate(wr.gpus, wr.node_off, wr.table, wr.claims)[0])
+    ref_out = ref_all[rank]
+    if got_all.tobytes() != np.concatenate(ref_all).tobytes():
         raise SystemExit("bench: CUDA result differs from the oracle — refusing to time a wrong kernel")
 
     # ---- device-resident throughput ---------------------------------------------------------------------
@@ -292,7 +314,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = CLAIMS_PER_RANK * world * args.steps / e2e_s
-    assert pin_o.array[rank * n_out:(rank + 1) * n_out].tobytes() == ref_out.tobytes()
+    assert pin_o.array.tobytes() == np.concatenate(ref_all).tobytes()
 
     line = None
     if rank == 0:
@@ -309,7 +331,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/u32 integer", "data": "synthetic",
-                "config": config(world),
+                "config": dict(config(world), **({"collective": collective} if collective else {})),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_claim,
                         "d2h_bytes_per_step": 8 * n_out * world, "timer": "host wall clock around the C-ABI call"},
                 "gpu_launches": launches,
@@ -339,6 +361,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nccl", action="store_true", help="N>1: use ncclAllGather instead of the peer-store all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -199,6 +199,16 @@ int  dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claim
                                       const uint32_t* d_out_off, dra_out_rec* d_out_all,
                                       uint32_t n_out, uint32_t n_per_rank, uint32_t flags);
 
+/* Peer-memory all-gather (NVLink P2P stores + epoch flags) — when set up, dra_allocate_batch_gather_device
+ * uses it instead of ncclAllGather.  Call after dra_comm_init on every rank:
+ *   dra_peer_export(ctx, n_per_rank, handle)   allocates this rank's gather buffer, returns its 64-byte
+ *                                              cudaIpcMemHandle_t;  the host runtime all-gathers the handles;
+ *   dra_peer_import(ctx, handles)              world * 64 bytes, in rank order.
+ * Requires all ranks on one node with P2P access; on failure the NCCL path stays in use.
+ * dra_peer_export(ctx, 0, NULL) switches the peer path off again. */
+int  dra_peer_export(dra_ctx* ctx, uint32_t n_per_rank, void* handle64);
+int  dra_peer_import(dra_ctx* ctx, const void* handles);
+
 /* ---- host memory + instrumentation ---------------------------------------------------------------- */
 
 /* Page-locked host buffers: passing these to the *_batch calls skips the internal staging copy. */

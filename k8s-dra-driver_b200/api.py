@@ -49,6 +49,8 @@ SYMBOLS = {
     "dra_comm_unique_id": (_i32, [_vp]),
     "dra_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
     "dra_allocate_batch_gather_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _u32]),
+    "dra_peer_export": (_i32, [_vp, _u32, _vp]),
+    "dra_peer_import": (_i32, [_vp, _vp]),
     "dra_host_alloc": (_vp, [C.c_size_t]),
     "dra_host_free": (None, [_vp]),
     "dra_launch_count": (_u64, [_vp]),
@@ -234,6 +236,19 @@ class Context:
     def comm_init(self, uid: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._check(self._lib.dra_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
+    def peer_disable(self) -> None:
+        self._check(self._lib.dra_peer_export(self._h, 0, None))
+
+    def peer_export(self, n_per_rank: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self._lib.dra_peer_export(self._h, n_per_rank, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peer_import(self, handles) -> None:
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.dra_peer_import(self._h, C.cast(buf, C.c_void_p)))
 
     # -- instrumentation ------------------------------------------------------------------------------
     def launch_count(self) -> int:

@@ -108,6 +108,14 @@ struct dra_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
 
+    // peer-memory all-gather
+    bool peer_ready = false;
+    uint32_t peer_n_per = 0, peer_epoch = 0;
+    size_t peer_bytes = 0, peer_flag_off = 0;
+    uint8_t* peer_local = nullptr;              // this rank's buffer (cudaMalloc)
+    uint8_t* peer_base[PEER_MAX] = {};          // every rank's buffer as mapped here
+    uint32_t* d_ticket = nullptr;
+
     std::string err;
 };
 
@@ -306,11 +314,12 @@ int collect_timings(dra_ctx* ctx, int n_marks) {
 }
 
 int check_err(dra_ctx* ctx) {
-    uint32_t oor = ctx->h_err[ERR_OUT_RANGE], ns = ctx->h_err[ERR_NOT_SORTED];
-    if (!oor && !ns) return DRA_OK;
+    uint32_t oor = ctx->h_err[ERR_OUT_RANGE], ns = ctx->h_err[ERR_NOT_SORTED], pt = ctx->h_err[ERR_PEER_TIMEOUT];
+    if (!oor && !ns && !pt) return DRA_OK;
     for (uint32_t i = 0; i < ERR_WORDS; ++i) ctx->h_err[i] = 0;
     cudaMemsetAsync(ctx->d_err, 0, ERR_WORDS * sizeof(uint32_t), ctx->stream);
     cudaStreamSynchronize(ctx->stream);
+    if (pt) return fail(ctx, DRA_E_NCCL, "peer all-gather: a rank did not publish its slice in time");
     if (ns) return fail(ctx, DRA_E_INVAL, "DRA_F_NODE_SORTED given but claims are not sorted by node; inventory unchanged");
     return fail(ctx, DRA_E_INVAL, "out_off/n_out: a claim's slots fall outside out[]; inventory state is undefined, reset it");
 }
@@ -367,6 +376,9 @@ void dra_ctx_destroy(dra_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) { std::lock_guard<std::mutex> lk(g_nccl_mu); if (g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm); }
+    for (int r = 0; r < (int)PEER_MAX; ++r) if (c->peer_base[r] && c->peer_base[r] != c->peer_local) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if (c->peer_local) cudaFree(c->peer_local);
+    if (c->d_ticket) cudaFree(c->d_ticket);
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
                    c->d_pair_pod, c->d_bits, c->d_err};
@@ -618,6 +630,47 @@ int dra_comm_init(dra_ctx* ctx, const void* id128, int rank, int world) {
     return DRA_OK;
 }
 
+int dra_peer_export(dra_ctx* ctx, uint32_t n_per_rank, void* handle64) {
+    if (!ctx) return DRA_E_INVAL;
+    if (!n_per_rank) { ctx->peer_ready = false; return DRA_OK; }          // switch the peer path off (NCCL again)
+    if (!handle64) return DRA_E_INVAL;
+    if (!ctx->comm) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called");
+    if (ctx->world > (int)PEER_MAX) return fail(ctx, DRA_E_INVAL, "world %d > %u", ctx->world, PEER_MAX);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->peer_ready = false;
+    if (ctx->peer_local) { CU(cudaFree(ctx->peer_local)); ctx->peer_local = nullptr; }
+    const uint32_t n_per = (n_per_rank + 1u) & ~1u;                       // slices are copied as uint4
+    const size_t data = (size_t)2 * ctx->world * n_per * 8;
+    ctx->peer_flag_off = (data + 255) & ~(size_t)255;
+    ctx->peer_bytes = ctx->peer_flag_off + 256;
+    CU(cudaMalloc((void**)&ctx->peer_local, ctx->peer_bytes));
+    CU(cudaMemset(ctx->peer_local, 0, ctx->peer_bytes));
+    if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemset(ctx->d_ticket, 0, 64)); }
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU(cudaIpcGetMemHandle(&h, ctx->peer_local));
+    memcpy(handle64, &h, 64);
+    ctx->peer_n_per = n_per; ctx->peer_epoch = 0;
+    return DRA_OK;
+}
+
+int dra_peer_import(dra_ctx* ctx, const void* handles) {
+    if (!ctx || !handles) return DRA_E_INVAL;
+    if (!ctx->peer_local) return fail(ctx, DRA_E_STATE, "dra_peer_export has not been called");
+    CU(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->world; ++r) {
+        if (r == ctx->rank) { ctx->peer_base[r] = ctx->peer_local; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, (const uint8_t*)handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, DRA_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e)); }
+        ctx->peer_base[r] = (uint8_t*)p;
+    }
+    ctx->peer_ready = true;
+    return DRA_OK;
+}
+
 int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                                      dra_out_rec* d_out_all, uint32_t n_out, uint32_t n_per_rank, uint32_t flags) {
     if (!ctx || !d_out_all || (n_claim && !d_claims)) return DRA_E_INVAL;
@@ -626,6 +679,33 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_batch(ctx, n_claim, n_out, false);
     if (rc) return rc;
+
+    if (ctx->peer_ready && ((n_per_rank + 1u) & ~1u) == ctx->peer_n_per && (n_per_rank & 1u) == 0) {
+        // ---- peer-memory all-gather: kernel writes its slice, push kernel stores it into every peer ----
+        const uint32_t n_per = ctx->peer_n_per;
+        ctx->peer_epoch += 1;
+        PeerArgs pa; memset(&pa, 0, sizeof pa);
+        for (int r = 0; r < ctx->world; ++r) {
+            pa.buf[r] = (uint4*)ctx->peer_base[r];
+            pa.flags[r] = (uint32_t*)(ctx->peer_base[r] + ctx->peer_flag_off);
+        }
+        pa.ticket = ctx->d_ticket; pa.world = ctx->world; pa.rank = ctx->rank; pa.n_per16 = n_per / 2;
+        pa.epoch = ctx->peer_epoch; pa.parity = ctx->peer_epoch & 1u; pa.err = err_of(ctx);
+        dra_out_rec* mine = (dra_out_rec*)ctx->peer_local + ((size_t)pa.parity * ctx->world + ctx->rank) * n_per;
+        if (n_per > n_out) CU(cudaMemsetAsync(mine + n_out, 0, (size_t)(n_per - n_out) * 8, ctx->stream));
+        rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags);
+        if (rc) return rc;
+        const uint32_t push_blocks = std::max(1u, std::min(32u, (pa.n_per16 + 255) / 256));
+        k_peer_push<<<push_blocks, 256, 0, ctx->stream>>>(pa);
+        const uint32_t wait_blocks = std::max(1u, std::min(64u, (pa.n_per16 * ctx->world + 255) / 256));
+        k_peer_wait<<<wait_blocks, 256, 0, ctx->stream>>>(pa, (uint4*)d_out_all);
+        ctx->launches += 2;
+        if (ctx->profiling) cudaEventRecord(ctx->ev[5], ctx->stream);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "peer all-gather launch: %s", cudaGetErrorString(e));
+        return DRA_OK;
+    }
+
     dra_out_rec* mine = d_out_all + (size_t)ctx->rank * n_per_rank;
     if (n_per_rank > n_out) CU(cudaMemsetAsync(mine + n_out, 0, (size_t)(n_per_rank - n_out) * 8, ctx->stream));
     rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags);

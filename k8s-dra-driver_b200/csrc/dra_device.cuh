@@ -29,6 +29,7 @@ constexpr uint32_t SEG = 32;          // claims per TMA segment
 constexpr uint32_t RING = 4;          // ring slots per warp
 constexpr uint32_t ERR_OUT_RANGE = 1u;    // index into the error-flag words
 constexpr uint32_t ERR_NOT_SORTED = 2u;
+constexpr uint32_t ERR_PEER_TIMEOUT = 3u;
 constexpr uint32_t ERR_WORDS = 4u;
 
 // Error flags: `dev` (device memory) gates later kernels of the same batch, `host` (mapped pinned
@@ -1102,6 +1103,69 @@ k_dealloc(const uint4* __restrict__ claims, uint32_t n_claim, const uint32_t* __
             while (old != assumed);
         }
     }
+}
+
+
+// ====================================================================================================
+// peer all-gather: the path's one collective as NVLink P2P stores instead of a library call
+// ====================================================================================================
+// Every rank owns a buffer  [2 parities][world][n_per] OutRec  + flag words, IPC-mapped into every peer.
+//   k_peer_push   this rank's slice -> the same slot of every peer's buffer (16-byte coalesced stores over
+//                 NVLink), system fence, then the last CTA publishes the epoch in every peer's flag word
+//   k_peer_wait   spins (bounded) until every rank's flag shows the epoch, then copies the complete table
+//                 to the caller's buffer
+// Parity alternates per call, so a rank can push epoch e+1 while a slow peer still reads epoch e.
+constexpr uint32_t PEER_MAX = 16;
+struct PeerArgs {
+    uint4* buf[PEER_MAX];         // peer buffers (buf[rank] is local)
+    uint32_t* flags[PEER_MAX];    // peer flag arrays, one word per source rank
+    uint32_t* ticket;             // local
+    uint32_t world, rank, n_per16; // n_per16 = uint4s per rank slice
+    uint32_t epoch, parity;
+    Err err;
+};
+
+__global__ void __launch_bounds__(256)
+k_peer_push(const PeerArgs a) {
+    const size_t slot = ((size_t)a.parity * a.world + a.rank) * a.n_per16;
+    const uint4* src = a.buf[a.rank] + slot;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t p = 0; p < a.world; ++p) {
+        if (p == a.rank) continue;
+        uint4* dst = a.buf[p] + slot;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_per16; i += stride) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(a.ticket, 1u);
+        if (t == gridDim.x - 1) {                       // every CTA's stores are fenced: publish
+            *a.ticket = 0;
+            __threadfence_system();
+            for (uint32_t p = 0; p < a.world; ++p)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[p] + a.rank), "r"(a.epoch) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_peer_wait(const PeerArgs a, uint4* __restrict__ user_out) {
+    if (threadIdx.x < a.world) {
+        const uint32_t* f = a.flags[a.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        uint32_t v;
+        bool ok = true;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int32_t)(v - a.epoch) >= 0) break;
+            if (clock64() - t0 > 400000000ll) { ok = false; break; }     // ~0.2 s: a peer is gone; fail, do not hang
+        } while (true);
+        if (!ok) a.err.set(ERR_PEER_TIMEOUT);
+    }
+    __syncthreads();
+    const uint4* src = a.buf[a.rank] + (size_t)a.parity * a.world * a.n_per16;
+    const uint32_t n = a.world * a.n_per16, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) user_out[i] = src[i];
 }
 
 }  // namespace dra
