@@ -175,6 +175,7 @@ def run_reference(args):
 
 
 def run_ours(args):
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("k8s-dra-driver_b200")

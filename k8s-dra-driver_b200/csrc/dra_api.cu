@@ -207,7 +207,7 @@ struct Prof {
 
 // The kernel chain of one Allocate batch on device-resident inputs.  Enqueues only.
 int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
-                    uint2* d_out, uint32_t n_out, uint32_t flags) {
+                    uint2* d_out, uint32_t n_out, uint32_t flags, const PeerTail* tail = nullptr, bool* tail_done = nullptr) {
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
     int rc = upload_table(ctx);
     if (rc) return rc;
@@ -231,6 +231,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     const bool fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) &&
                        (uint64_t)n_node * n_claim <= ctx->fused_max_work && fused_smem <= 220 * 1024 && n_node <= 16384;
     if (fused) {
+        if (tail) { a.peer = *tail; if (tail_done) *tail_done = true; }
         if (fused_smem > 48 * 1024 && ctx->fused_smem_set < (int)fused_smem) {
             CU(cudaFuncSetAttribute(k_fused<FUSED_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
             ctx->fused_smem_set = (int)fused_smem;
@@ -693,13 +694,25 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
         pa.epoch = ctx->peer_epoch; pa.parity = ctx->peer_epoch & 1u; pa.err = err_of(ctx);
         dra_out_rec* mine = (dra_out_rec*)ctx->peer_local + ((size_t)pa.parity * ctx->world + ctx->rank) * n_per;
         if (n_per > n_out) CU(cudaMemsetAsync(mine + n_out, 0, (size_t)(n_per - n_out) * 8, ctx->stream));
-        rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags);
+        // preferred: the collective rides in the tail of the fused kernel (no extra launch)
+        PeerTail tail; memset(&tail, 0, sizeof tail);
+        for (int r = 0; r < ctx->world; ++r) {
+            tail.peer_out[r] = (uint2*)((dra_out_rec*)ctx->peer_base[r] + ((size_t)pa.parity * ctx->world + ctx->rank) * n_per);
+            tail.flags[r] = pa.flags[r];
+        }
+        tail.table = (const uint4*)((dra_out_rec*)ctx->peer_local + (size_t)pa.parity * ctx->world * n_per);
+        tail.user_out = (uint4*)d_out_all;
+        tail.ticket = ctx->d_ticket; tail.world = ctx->world; tail.rank = ctx->rank; tail.n_per16 = n_per / 2; tail.epoch = pa.epoch;
+        bool tail_done = false;
+        rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags, &tail, &tail_done);
         if (rc) return rc;
-        const uint32_t push_blocks = std::max(1u, std::min(32u, (pa.n_per16 + 255) / 256));
-        k_peer_push<<<push_blocks, 256, 0, ctx->stream>>>(pa);
-        const uint32_t wait_blocks = std::max(1u, std::min(64u, (pa.n_per16 * ctx->world + 255) / 256));
-        k_peer_wait<<<wait_blocks, 256, 0, ctx->stream>>>(pa, (uint4*)d_out_all);
-        ctx->launches += 2;
+        if (!tail_done) {                                   // sort path: separate push / wait kernels
+            const uint32_t push_blocks = std::max(1u, std::min(32u, (pa.n_per16 + 255) / 256));
+            k_peer_push<<<push_blocks, 256, 0, ctx->stream>>>(pa);
+            const uint32_t wait_blocks = std::max(1u, std::min(64u, (pa.n_per16 * ctx->world + 255) / 256));
+            k_peer_wait<<<wait_blocks, 256, 0, ctx->stream>>>(pa, (uint4*)d_out_all);
+            ctx->launches += 2;
+        }
         if (ctx->profiling) cudaEventRecord(ctx->ev[5], ctx->stream);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "peer all-gather launch: %s", cudaGetErrorString(e));

@@ -573,6 +573,17 @@ k_sorted_prep(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_nod
 // pack: first-fit per node
 // ====================================================================================================
 
+// Tail of k_fused in multi-GPU mode: the path's one collective done with NVLink P2P stores, no extra launch.
+constexpr uint32_t PEER_MAX = 16;
+struct PeerTail {
+    uint2* peer_out[PEER_MAX];    // this rank's slice inside every rank's gather buffer (peer_out[rank] == out)
+    uint32_t* flags[PEER_MAX];    // every rank's flag array (one word per source rank)
+    const uint4* table;           // local gather buffer, current parity: [world][n_per16] uint4
+    uint4* user_out;              // where the caller wants the complete table (may be NULL)
+    uint32_t* ticket;
+    uint32_t world, rank, n_per16, epoch;
+};
+
 struct PackArgs {
     const uint4* sorted;          // node-sorted claims, .y = first out slot          (k_pack)
     const uint32_t* claim_off;    // [n_node+2]                                        (k_pack)
@@ -586,6 +597,7 @@ struct PackArgs {
     uint2* out;
     uint32_t n_out, n_node, have_off;
     Err err;
+    PeerTail peer;                // world == 0: single GPU                            (k_fused)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
@@ -975,8 +987,11 @@ k_fused(const PackArgs a) {
                     const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
                     const uint32_t kind = c.x & 0xFFu;
                     const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
-                    if (dst < a.n_out) a.out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
-                    else a.err.set(ERR_OUT_RANGE);
+                    if (dst < a.n_out) {
+                        const uint2 r_ = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+                        a.out[dst] = r_;
+                        for (uint32_t p = 0; p < a.peer.world; ++p) if (p != a.peer.rank) a.peer.peer_out[p][dst] = r_;
+                    } else a.err.set(ERR_OUT_RANGE);
                 }
             }
         }
@@ -985,48 +1000,95 @@ k_fused(const PackArgs a) {
     }
     if (lane == 0) sts32(sbase + FU_CNT + (wid << 2), cntw);
     __syncthreads();
-    if (wid != 0 || !has_node) return;
 
-    // ---- pack: warp 0 ----------------------------------------------------------------------------------
     IdxGet<NW> get;
     get.claims = a.claims; get.out_off = a.out_off; get.list_addr = list_addr; get.chunk = chunk;
     uint32_t cnt = 0;
     #pragma unroll
     for (int i = 0; i < NW; ++i) { get.pre[i] = cnt; cnt += lds32(sbase + FU_CNT + (i << 2)); }
-    if (cnt == 0) {
-        if (a.inv_src != a.inv_dst && lane < ng) a.inv_dst[g0 + lane] = __ldg(&a.inv_src[g0 + lane]);
-        return;
-    }
-    // the first segment's claims are requested before waiting for the table / inventory
-    auto fetch = [&](uint32_t seg, uint4& c, bool& present) {
-        const uint32_t m = seg * SEG + lane;
-        present = m < cnt;
-        c = make_uint4(0xFFu, 0, 0, 0);
-        if (present) c = get(m);
-    };
-    uint4 c_cur; bool p_cur;
-    fetch(0, c_cur, p_cur);
 
-    NodeCtx x;
-    x.lane = lane; x.ltmask = ltmask;
-    x.live_addr = sbase + FU_LIVE; x.tbl_addr = sbase + FU_TBL;
-    x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + FU_TBL);
-    x.have_off = a.have_off != 0;
-    x.sink = OutSink{a.out, a.n_out, a.err, lane};
-    x.g0 = g0;
-    mbar_wait_a(tbar, 0);
-    uint4 rec = make_uint4(0, 0, 0, 0);
-    if (ng) { mbar_wait_a(ibar, 0); if (lane < ng) rec = lds128(sbase + FU_INV + lane * 16); }
-    x.begin(rec, lane < ng);
+    // ---- pack: warp 0 ----------------------------------------------------------------------------------
+    if (wid == 0 && has_node) {
+        if (cnt == 0) {
+            if (a.inv_src != a.inv_dst && lane < ng) a.inv_dst[g0 + lane] = __ldg(&a.inv_src[g0 + lane]);
+        } else {
+            // the first segment's claims are requested before waiting for the table / inventory
+            auto fetch = [&](uint32_t seg, uint4& c, bool& present) {
+                const uint32_t m = seg * SEG + lane;
+                present = m < cnt;
+                c = make_uint4(0xFFu, 0, 0, 0);
+                if (present) c = get(m);
+            };
+            uint4 c_cur; bool p_cur;
+            fetch(0, c_cur, p_cur);
 
-    const uint32_t nseg = (cnt + SEG - 1) / SEG;
-    for (uint32_t seg = 0; seg < nseg; ++seg) {
-        uint4 c_nxt = make_uint4(0xFFu, 0, 0, 0); bool p_nxt = false;
-        if (seg + 1 < nseg) fetch(seg + 1, c_nxt, p_nxt);       // in flight while this segment is packed
-        segment_run(x, c_cur, p_cur, seg * SEG + lane, get, cnt);
-        c_cur = c_nxt; p_cur = p_nxt;
+            NodeCtx x;
+            x.lane = lane; x.ltmask = ltmask;
+            x.live_addr = sbase + FU_LIVE; x.tbl_addr = sbase + FU_TBL;
+            x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + FU_TBL);
+            x.have_off = a.have_off != 0;
+            x.sink = OutSink{a.out, a.n_out, a.err, lane};
+            x.g0 = g0;
+            mbar_wait_a(tbar, 0);
+            uint4 rec = make_uint4(0, 0, 0, 0);
+            if (ng) { mbar_wait_a(ibar, 0); if (lane < ng) rec = lds128(sbase + FU_INV + lane * 16); }
+            x.begin(rec, lane < ng);
+
+            const uint32_t nseg = (cnt + SEG - 1) / SEG;
+            for (uint32_t seg = 0; seg < nseg; ++seg) {
+                uint4 c_nxt = make_uint4(0xFFu, 0, 0, 0); bool p_nxt = false;
+                if (seg + 1 < nseg) fetch(seg + 1, c_nxt, p_nxt);       // in flight while this segment is packed
+                segment_run(x, c_cur, p_cur, seg * SEG + lane, get, cnt);
+                c_cur = c_nxt; p_cur = p_nxt;
+            }
+            if (lane < ng) a.inv_dst[g0 + lane] = x.L.store(rec);
+        }
     }
-    if (lane < ng) a.inv_dst[g0 + lane] = x.L.store(rec);
+    if (a.peer.world == 0) return;
+
+    // ---- multi-GPU tail: all-gather by peer stores, fused here (no extra launch) -------------------------
+    // 1. every CTA pushes the OutRecs of ITS node's claims into the same slots of every peer's table
+    __syncthreads();                                   // warp 0's OutRecs are visible to the whole CTA
+    const PeerTail& pt = a.peer;
+    if (has_node) {
+        for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
+            const uint32_t i = get.index_of(m);
+            const uint4 c = __ldg(&a.claims[i]);
+            const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
+            const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
+            const uint32_t slots = (kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
+            if (dst > a.n_out || slots > a.n_out - dst) continue;
+            for (uint32_t s_ = 0; s_ < slots; ++s_) {
+                const uint2 r_ = a.out[dst + s_];
+                for (uint32_t p = 0; p < pt.world; ++p) if (p != pt.rank) pt.peer_out[p][dst + s_] = r_;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. the last CTA to get here publishes this rank's epoch to every peer, waits for theirs, copies the table
+    __shared__ uint32_t last_s;
+    if (threadIdx.x == 0) last_s = atomicAdd(pt.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) *pt.ticket = 0;
+    if (threadIdx.x < pt.world) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[threadIdx.x] + pt.rank), "r"(pt.epoch) : "memory");
+        const uint32_t* f = pt.flags[pt.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int32_t)(v - pt.epoch) >= 0) break;
+            if (clock64() - t0 > 400000000ll) { a.err.set(ERR_PEER_TIMEOUT); break; }   // ~0.2 s: fail, do not hang
+        } while (true);
+    }
+    __syncthreads();
+    if (pt.user_out) {
+        const uint32_t n = pt.world * pt.n_per16;
+        for (uint32_t i = threadIdx.x; i < n; i += NW * 32) pt.user_out[i] = pt.table[i];
+    }
 }
 
 // ====================================================================================================
@@ -1115,7 +1177,6 @@ k_dealloc(const uint4* __restrict__ claims, uint32_t n_claim, const uint32_t* __
 //   k_peer_wait   spins (bounded) until every rank's flag shows the epoch, then copies the complete table
 //                 to the caller's buffer
 // Parity alternates per call, so a rank can push epoch e+1 while a slow peer still reads epoch e.
-constexpr uint32_t PEER_MAX = 16;
 struct PeerArgs {
     uint4* buf[PEER_MAX];         // peer buffers (buf[rank] is local)
     uint32_t* flags[PEER_MAX];    // peer flag arrays, one word per source rank
