@@ -226,9 +226,11 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     F = pkg.api.F_FRESH_INVENTORY
 
+    peer = collective is not None and collective.startswith("peer")
+
     def step_dev():
-        if world > 1:
-            ctx.allocate_gather_device(d_claims.data_ptr(), n_claim, None, d_out_all.data_ptr(), n_out, n_out, F)
+        if world > 1:     # peer mode: the table stays in the context's IPC-mapped buffer (no copy out)
+            ctx.allocate_gather_device(d_claims.data_ptr(), n_claim, None, None if peer else d_out_all.data_ptr(), n_out, n_out, F)
         else:
             ctx.allocate_device(d_claims.data_ptr(), n_claim, None, d_out_all.data_ptr(), n_out, F)
 
@@ -240,7 +242,10 @@ def run_ours(args):
     # ---- parity guard: the timed path must produce the oracle's bytes --------------------------------
     from oracle import oracle as O
     step_dev(); ctx.sync()
-    got_all = d_out_all.cpu().numpy().view(R.OUT_DTYPE)
+    if world > 1:
+        got_all = ctx.gather_read(np.zeros(world * n_out, dtype=R.OUT_DTYPE))
+    else:
+        got_all = d_out_all.cpu().numpy().view(R.OUT_DTYPE)
     ref_all = []
     for r in range(world):                       # every rank checks the WHOLE gathered table
         wr = w if r == rank else workload(pkg, r, world)
@@ -299,8 +304,7 @@ def run_ours(args):
         else:
             d_claims.copy_(h_claims_t, non_blocking=True)
             step_dev()
-            h_out_t.copy_(d_out_all, non_blocking=True)
-            ctx.sync()
+            ctx.gather_read(pin_o.array)
 
     for _ in range(max(3, args.warmup)):
         step_e2e()

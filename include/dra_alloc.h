@@ -199,6 +199,12 @@ int  dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claim
                                       const uint32_t* d_out_off, dra_out_rec* d_out_all,
                                       uint32_t n_out, uint32_t n_per_rank, uint32_t flags);
 
+/* The complete table of the last gather: device pointer (valid until the second-next gather call) and the
+ * padded per-rank length; with the peer all-gather set up d_out_all may be NULL and this is the result. */
+int  dra_gather_table(dra_ctx* ctx, const dra_out_rec** d_table, uint32_t* n_per_rank);
+/* Device -> host read of the first n_rec records of that table on ctx's stream, then synchronises. */
+int  dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec);
+
 /* Peer-memory all-gather (NVLink P2P stores + epoch flags) — when set up, dra_allocate_batch_gather_device
  * uses it instead of ncclAllGather.  Call after dra_comm_init on every rank:
  *   dra_peer_export(ctx, n_per_rank, handle)   allocates this rank's gather buffer, returns its 64-byte

@@ -49,6 +49,8 @@ SYMBOLS = {
     "dra_comm_unique_id": (_i32, [_vp]),
     "dra_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
     "dra_allocate_batch_gather_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _u32]),
+    "dra_gather_table": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_u32)]),
+    "dra_gather_read": (_i32, [_vp, _vp, _u32]),
     "dra_peer_export": (_i32, [_vp, _u32, _vp]),
     "dra_peer_import": (_i32, [_vp, _vp]),
     "dra_host_alloc": (_vp, [C.c_size_t]),
@@ -236,6 +238,11 @@ class Context:
     def comm_init(self, uid: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._check(self._lib.dra_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
+    def gather_read(self, out_all: np.ndarray) -> np.ndarray:
+        """D2H of the last gather's table into out_all (OUT_DTYPE, world * n_per_rank); synchronises."""
+        self._check(self._lib.dra_gather_read(self._h, _ptr(out_all), len(out_all)))
+        return out_all
 
     def peer_disable(self) -> None:
         self._check(self._lib.dra_peer_export(self._h, 0, None))

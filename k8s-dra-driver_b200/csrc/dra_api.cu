@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -115,6 +116,8 @@ struct dra_ctx {
     uint8_t* peer_local = nullptr;              // this rank's buffer (cudaMalloc)
     uint8_t* peer_base[PEER_MAX] = {};          // every rank's buffer as mapped here
     uint32_t* d_ticket = nullptr;
+    const dra_out_rec* gather_table = nullptr;  // where the last gather's complete table lives (device)
+    uint32_t gather_n_per = 0;
 
     std::string err;
 };
@@ -674,8 +677,9 @@ int dra_peer_import(dra_ctx* ctx, const void* handles) {
 
 int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                                      dra_out_rec* d_out_all, uint32_t n_out, uint32_t n_per_rank, uint32_t flags) {
-    if (!ctx || !d_out_all || (n_claim && !d_claims)) return DRA_E_INVAL;
+    if (!ctx || (n_claim && !d_claims)) return DRA_E_INVAL;
     if (!ctx->comm) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called");
+    if (!d_out_all && !ctx->peer_ready) return fail(ctx, DRA_E_INVAL, "d_out_all may be NULL only with the peer all-gather set up");
     if (n_out > n_per_rank) return fail(ctx, DRA_E_INVAL, "n_out %u > n_per_rank %u", n_out, n_per_rank);
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_batch(ctx, n_claim, n_out, false);
@@ -700,18 +704,20 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
             tail.peer_out[r] = (uint2*)((dra_out_rec*)ctx->peer_base[r] + ((size_t)pa.parity * ctx->world + ctx->rank) * n_per);
             tail.flags[r] = pa.flags[r];
         }
-        tail.table = (const uint4*)((dra_out_rec*)ctx->peer_local + (size_t)pa.parity * ctx->world * n_per);
-        tail.user_out = (uint4*)d_out_all;
         tail.ticket = ctx->d_ticket; tail.world = ctx->world; tail.rank = ctx->rank; tail.n_per16 = n_per / 2; tail.epoch = pa.epoch;
         bool tail_done = false;
         rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags, &tail, &tail_done);
         if (rc) return rc;
+        const dra_out_rec* table = (const dra_out_rec*)ctx->peer_local + (size_t)pa.parity * ctx->world * n_per;
+        ctx->gather_table = table; ctx->gather_n_per = n_per;
         if (!tail_done) {                                   // sort path: separate push / wait kernels
             const uint32_t push_blocks = std::max(1u, std::min(32u, (pa.n_per16 + 255) / 256));
             k_peer_push<<<push_blocks, 256, 0, ctx->stream>>>(pa);
             const uint32_t wait_blocks = std::max(1u, std::min(64u, (pa.n_per16 * ctx->world + 255) / 256));
             k_peer_wait<<<wait_blocks, 256, 0, ctx->stream>>>(pa, (uint4*)d_out_all);
             ctx->launches += 2;
+        } else if (d_out_all) {                             // caller wants its own copy: one D2D copy node
+            CU(cudaMemcpyAsync(d_out_all, table, (size_t)ctx->world * n_per * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         }
         if (ctx->profiling) cudaEventRecord(ctx->ev[5], ctx->stream);
         cudaError_t e = cudaGetLastError();
@@ -719,6 +725,8 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
         return DRA_OK;
     }
 
+    if (!d_out_all) return fail(ctx, DRA_E_INVAL, "d_out_all is required on the NCCL path");
+    ctx->gather_table = d_out_all; ctx->gather_n_per = n_per_rank;
     dra_out_rec* mine = d_out_all + (size_t)ctx->rank * n_per_rank;
     if (n_per_rank > n_out) CU(cudaMemsetAsync(mine + n_out, 0, (size_t)(n_per_rank - n_out) * 8, ctx->stream));
     rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags);
@@ -727,6 +735,30 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     ncclResult_t r = g_nccl.AllGather(mine, d_out_all, (size_t)n_per_rank * 8, ncclUint8, ctx->comm, ctx->stream);
     if (r != ncclSuccess) return fail(ctx, DRA_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     if (ctx->profiling) cudaEventRecord(ctx->ev[5], ctx->stream);
+    return DRA_OK;
+}
+
+int dra_gather_table(dra_ctx* ctx, const dra_out_rec** d_table, uint32_t* n_per_rank) {
+    if (!ctx || !d_table) return DRA_E_INVAL;
+    if (!ctx->gather_table) return fail(ctx, DRA_E_STATE, "no gather has run");
+    *d_table = ctx->gather_table;
+    if (n_per_rank) *n_per_rank = ctx->gather_n_per;
+    return DRA_OK;
+}
+
+int dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec) {
+    if (!ctx || !out_all) return DRA_E_INVAL;
+    if (!ctx->gather_table) return fail(ctx, DRA_E_STATE, "no gather has run");
+    if (n_rec > (uint32_t)ctx->world * ctx->gather_n_per) return fail(ctx, DRA_E_INVAL, "n_rec %u exceeds the table", n_rec);
+    CU(cudaSetDevice(ctx->device));
+    const size_t rb = (size_t)n_rec * 8;
+    const bool direct = is_pinned(out_all, rb);
+    int rc;
+    if (!direct && (rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, rb))) return rc;
+    CU(cudaMemcpyAsync(direct ? (void*)out_all : (void*)ctx->h_out, ctx->gather_table, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if ((rc = check_err(ctx))) return rc;
+    if (!direct) memcpy(out_all, ctx->h_out, rb);
     return DRA_OK;
 }
 

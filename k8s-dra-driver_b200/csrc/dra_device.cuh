@@ -578,8 +578,6 @@ constexpr uint32_t PEER_MAX = 16;
 struct PeerTail {
     uint2* peer_out[PEER_MAX];    // this rank's slice inside every rank's gather buffer (peer_out[rank] == out)
     uint32_t* flags[PEER_MAX];    // every rank's flag array (one word per source rank)
-    const uint4* table;           // local gather buffer, current parity: [world][n_per16] uint4
-    uint4* user_out;              // where the caller wants the complete table (may be NULL)
     uint32_t* ticket;
     uint32_t world, rank, n_per16, epoch;
 };
@@ -1064,15 +1062,18 @@ k_fused(const PackArgs a) {
             }
         }
     }
-    __threadfence_system();
     __syncthreads();
-    // 2. the last CTA to get here publishes this rank's epoch to every peer, waits for theirs, copies the table
+    // 2. the last CTA to get here publishes this rank's epoch to every peer and waits for theirs.
+    //    One system fence per CTA: bar.sync orders the CTA's stores before thread 0, fences are cumulative.
     __shared__ uint32_t last_s;
-    if (threadIdx.x == 0) last_s = atomicAdd(pt.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last_s = atomicAdd(pt.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
     __syncthreads();
     if (!last_s) return;
-    __threadfence_system();
-    if (threadIdx.x == 0) *pt.ticket = 0;
+    if (threadIdx.x == 0) { *pt.ticket = 0; __threadfence_system(); }
+    __syncthreads();
     if (threadIdx.x < pt.world) {
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[threadIdx.x] + pt.rank), "r"(pt.epoch) : "memory");
         const uint32_t* f = pt.flags[pt.rank] + threadIdx.x;
@@ -1083,11 +1084,6 @@ k_fused(const PackArgs a) {
             if ((int32_t)(v - pt.epoch) >= 0) break;
             if (clock64() - t0 > 400000000ll) { a.err.set(ERR_PEER_TIMEOUT); break; }   // ~0.2 s: fail, do not hang
         } while (true);
-    }
-    __syncthreads();
-    if (pt.user_out) {
-        const uint32_t n = pt.world * pt.n_per16;
-        for (uint32_t i = threadIdx.x; i < n; i += NW * 32) pt.user_out[i] = pt.table[i];
     }
 }
 
