@@ -227,6 +227,11 @@ uint64_t dra_launch_count(const dra_ctx* ctx);
  * call's per-stage device times in microseconds: [0] bucket-hist [1] bucket-scan [2] bucket-scatter
  * [3] pack [4] all-gather.  Returns the number of floats written. */
 int  dra_set_profiling(dra_ctx* ctx, int enabled);
+/* Instrumentation (env DRA_TIMELINE=1): 8 clock stamps per CTA of the last single-launch kernel; returns the
+ * number of u64 words copied to host. */
+int  dra_debug_timeline(dra_ctx* ctx, unsigned long long* host, uint32_t n);
+/* Instrumentation: enqueue an empty kernel of the given shape on ctx's stream (launch-floor calibration). */
+int  dra_debug_noop(dra_ctx* ctx, uint32_t grid, uint32_t block, uint32_t smem_bytes);
 int  dra_get_timings(dra_ctx* ctx, float* us, int n);
 
 #ifdef __cplusplus

@@ -57,6 +57,8 @@ SYMBOLS = {
     "dra_host_free": (None, [_vp]),
     "dra_launch_count": (_u64, [_vp]),
     "dra_set_profiling": (_i32, [_vp, _i32]),
+    "dra_debug_timeline": (_i32, [_vp, _vp, _u32]),
+    "dra_debug_noop": (_i32, [_vp, _u32, _u32, _u32]),
     "dra_get_timings": (_i32, [_vp, _vp, _i32]),
 }
 
@@ -263,6 +265,14 @@ class Context:
 
     def set_profiling(self, on: bool):
         self._check(self._lib.dra_set_profiling(self._h, 1 if on else 0))
+
+    def debug_noop(self, grid: int, block: int, smem: int) -> None:
+        self._check(self._lib.dra_debug_noop(self._h, grid, block, smem))
+
+    def debug_timeline(self, n_cta: int) -> np.ndarray:
+        buf = np.zeros(n_cta * 8, dtype=np.uint64)
+        n = self._lib.dra_debug_timeline(self._h, _ptr(buf), len(buf))
+        return buf[:n].reshape(-1, 8)
 
     def timings_us(self) -> dict:
         buf = (C.c_float * 5)()

@@ -103,7 +103,7 @@ struct dra_ctx {
     cudaEvent_t ev[8] = {};
     bool ev_ok = false;
     float timings[5] = {0, 0, 0, 0, 0};
-    int hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0;
+    int hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0, fused_smem_set_stage = 0;
     uint64_t fused_max_work = 6000000ull;   // n_node * n_claim up to which the single-launch kernel is used
 
     ncclComm_t comm = nullptr;
@@ -116,6 +116,7 @@ struct dra_ctx {
     uint8_t* peer_local = nullptr;              // this rank's buffer (cudaMalloc)
     uint8_t* peer_base[PEER_MAX] = {};          // every rank's buffer as mapped here
     uint32_t* d_ticket = nullptr;
+    unsigned long long* d_timeline = nullptr; size_t tl_cap = 0; uint32_t tl_n = 0;
     const dra_out_rec* gather_table = nullptr;  // where the last gather's complete table lives (device)
     uint32_t gather_n_per = 0;
 
@@ -230,18 +231,33 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     // Small batches: ONE launch.  Every node's CTA filters the claim stream for itself (n_node * n_claim key
     // tests spread over n_node SMs, data from L2) and packs — no sort, no sorted copy.
     constexpr int FUSED_NW = 8;
-    const size_t fused_smem = fused_smem_bytes(n_claim, FUSED_NW);
+    static const bool no_stage = getenv("DRA_NO_STAGE") != nullptr;          // experiment switch
+    const bool stage = !no_stage && n_claim <= FUSED_NW * FU_PIECE * FU_MAXPIECE && fused_smem_bytes(n_claim, FUSED_NW, true) <= 225 * 1024;
+    const size_t fused_smem = fused_smem_bytes(n_claim, FUSED_NW, stage);
     const bool fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) &&
-                       (uint64_t)n_node * n_claim <= ctx->fused_max_work && fused_smem <= 220 * 1024 && n_node <= 16384;
+                       (uint64_t)n_node * n_claim <= ctx->fused_max_work && fused_smem <= 225 * 1024 && n_node <= 16384;
     if (fused) {
         if (tail) { a.peer = *tail; if (tail_done) *tail_done = true; }
-        if (fused_smem > 48 * 1024 && ctx->fused_smem_set < (int)fused_smem) {
-            CU(cudaFuncSetAttribute(k_fused<FUSED_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-            ctx->fused_smem_set = (int)fused_smem;
+        int& set = stage ? ctx->fused_smem_set_stage : ctx->fused_smem_set;
+        if (fused_smem > 48 * 1024 && set < (int)fused_smem) {
+            if (stage) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            else CU(cudaFuncSetAttribute(k_fused<FUSED_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            set = (int)fused_smem;
         }
         a.claims = d_claims; a.out_off = d_out_off; a.n_claim = n_claim;
+        if (getenv("DRA_TIMELINE")) {           // instrumentation only: per-CTA clock stamps of the last fused launch
+            if (ctx->tl_cap < (size_t)(n_node + 1) * 8) {
+                if (ctx->d_timeline) CU(cudaFree(ctx->d_timeline));
+                ctx->tl_cap = (size_t)(n_node + 1) * 8 + 64;
+                CU(cudaMalloc((void**)&ctx->d_timeline, ctx->tl_cap * 8));
+            }
+            CU(cudaMemsetAsync(ctx->d_timeline, 0, ctx->tl_cap * 8, ctx->stream));
+            a.timeline = ctx->d_timeline; ctx->tl_n = (n_node + 1) * 8;
+        }
         prof.mark(); prof.mark(); prof.mark();
-        k_fused<FUSED_NW><<<std::max(n_node, 1u), FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
+        // grid = one CTA per node + one CTA for the claims that name no node
+        if (stage) k_fused<FUSED_NW, true><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
+        else k_fused<FUSED_NW, false><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
         ctx->launches += 1;
         prof.mark();
         cudaError_t e = cudaGetLastError();
@@ -779,6 +795,26 @@ void dra_host_free(void* p) {
 }
 
 uint64_t dra_launch_count(const dra_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+namespace { __global__ void k_noop(int x) { extern __shared__ uint8_t sm[]; if (x == 12345) sm[0] = 1; } }
+
+// Instrumentation: enqueue an empty kernel with the given shape (calibrates the launch floor of the box).
+int dra_debug_noop(dra_ctx* ctx, uint32_t grid, uint32_t block, uint32_t smem) {
+    if (!ctx) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_noop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_noop<<<grid, block, smem, ctx->stream>>>(0);
+    return DRA_OK;
+}
+
+int dra_debug_timeline(dra_ctx* ctx, unsigned long long* host, uint32_t n) {
+    if (!ctx || !host || !ctx->d_timeline) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    uint32_t m = std::min(n, ctx->tl_n);
+    cudaMemcpy(host, ctx->d_timeline, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    return (int)m;
+}
 
 int dra_set_profiling(dra_ctx* ctx, int enabled) {
     if (!ctx) return DRA_E_INVAL;

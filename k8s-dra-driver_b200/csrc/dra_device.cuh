@@ -303,6 +303,15 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
     return 1;
 }
 
+// Out-of-line copy for the pack kernels: co-location runs are rare there, and keeping ~900 instructions out
+// of the hot loop's instruction-cache footprint matters more than the call (the kernel runs once per SM).
+template <class Get, class Sink>
+__device__ __noinline__ uint32_t node_step_cold(Lane& L, Dead& D, uint32_t lane, uint32_t g0,
+                                                const uint32_t* __restrict__ tbl_s, Get get, uint32_t k,
+                                                uint32_t cnt, Sink& sink, bool have_off) {
+    return node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, have_off);
+}
+
 // ====================================================================================================
 // bucketing: stable counting sort of claims by node
 // ====================================================================================================
@@ -596,6 +605,7 @@ struct PackArgs {
     uint32_t n_out, n_node, have_off;
     Err err;
     PeerTail peer;                // world == 0: single GPU                            (k_fused)
+    unsigned long long* timeline; // optional instrumentation: 8 clock stamps per CTA  (k_fused), else NULL
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
@@ -603,6 +613,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts32_if(bool p, uint32_t addr, uint32_t v) {     // predicated, no branch
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -654,10 +667,12 @@ struct NodeCtx {
     Lane L; Dead D; OutSink sink;
     uint32_t lane, ltmask, g0, m0, k_next;
     uint32_t gate;                 // 0xFFFF on lanes whose GPU can take MIG devices at all, else 0
-    uint32_t live_addr;            // shared: 32 prepared records x 32 B
+    uint32_t live_addr;            // shared: 32 prepared records x 32 B, followed by 32 result words
     uint32_t tbl_addr;             // shared: placement table (u32 cells)
     const uint32_t* tbl_ptr;       // same table for the generic step
     bool homog, mig_ok, mig_offer, have_off;
+    bool prof_on = false;          // instrumentation: cycle accumulators of the three parts of segment_run
+    long long t_pre = 0, t_loop = 0, t_epi = 0; uint32_t n_live = 0;
 
     __device__ __forceinline__ void begin(uint4 rec, bool valid) {
         constexpr uint32_t BLOCKED = DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE;
@@ -684,6 +699,7 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     constexpr uint32_t BLOCKED = DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE;
     Lane& L = x.L; Dead& D = x.D; OutSink& sink = x.sink;
     const uint32_t lane = x.lane, g0 = x.g0;
+    long long tq0 = 0; if (x.prof_on) tq0 = clock64();
     const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
     const uint32_t dst = c.y, mem = c.z, group = c.w;
     bool live = present && pos >= x.k_next;
@@ -730,22 +746,26 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     }
     __syncwarp();
     const uint32_t nlive = (uint32_t)__popc(lm);
+    long long tq1 = 0; if (x.prof_on) { tq1 = clock64(); x.t_pre += tq1 - tq0; x.n_live += nlive; }
 
-    // one live record; returns nothing, mutates L / D.  Success path of every class is branch-free.
-    auto step = [&](const uint4 r0, const uint4 r1) {
+    // One live record: mutates L / D.  MIG and SHARED steps only RECORD their outcome in shared memory
+    // (res[q] = winner lane | start<<8 | size<<16, or 0xFF | status<<24); the OutRecs are composed and stored
+    // after the loop, 32 at a time — nothing but the first-fit chain itself stays on the serial path.
+    const uint32_t res_addr = x.live_addr + 1024;
+    auto step = [&](const uint4 r0, const uint4 r1, const uint32_t q) {
         const uint32_t cls = r1.x >> 24, dj = r1.y;
         if (cls == 1u) {                                   // MIG, spec §5
             const uint32_t pj = (r1.x >> 16) & 0xFFu;
             if (((D.bad | D.nocap) >> pj) & 1u) {          // shape died earlier in this segment
-                if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, pj, ((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY));
+                if (lane == 0) sts32(res_addr + (q << 2), 0xFFu | ((((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY) << 24));
                 return;
             }
-            uint32_t smask = r1.x & 0xFFFFu, s1 = r0.x, s2 = r0.y, s3 = r0.z, s4 = r0.w, mm = r1.z, sbits = r1.w;
+            uint32_t smask = r1.x & 0xFFFFu, s1 = r0.x, s2 = r0.y, s3 = r0.z, s4 = r0.w, sbits = r1.w, size = (r1.z >> 8) & 0xFFu;
             if (!x.homog) {                                // per-GPU table row
                 const uint32_t e = lds32(x.tbl_addr + ((L.model * DRA_MAX_PROFILES + pj) << 2));
-                const uint32_t size = e & 0xFFu, sh = shifts_of(size);
-                smask = e >> 16; s1 = sh & 15u; s2 = (sh >> 4) & 15u; s3 = (sh >> 8) & 15u; s4 = sh >> 12;
-                mm = (size << 8) | (pj << 16); sbits = (1u << size) - 1u;
+                const uint32_t sh = shifts_of(e & 0xFFu);
+                size = e & 0xFFu; smask = e >> 16; s1 = sh & 15u; s2 = (sh >> 4) & 15u; s3 = (sh >> 8) & 15u; s4 = sh >> 12;
+                sbits = (1u << size) - 1u;
             }
             uint32_t t = ~L.busy & x.gate;
             t &= t >> s1; t &= t >> s2; t &= t >> s3; t &= t >> s4;
@@ -753,13 +773,13 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
             const uint32_t st = (uint32_t)__ffs(cand) - 1u;              // lowest start (if this lane wins)
             const bool win = lane == (uint32_t)__ffs(b) - 1u;            // lowest GPU; b == 0: nobody
-            if (win) { L.busy |= sbits << (st & 31u); sink.put(dj, g0 + lane, mm | st); }
+            if (win) { L.busy |= sbits << (st & 31u); sts32(res_addr + (q << 2), lane | (st << 8) | (size << 16)); }
             if (b == 0) {
                 const bool any = __ballot_sync(FULLMASK, x.mig_offer && smask != 0) != 0;
                 if (any) D.nocap |= 1u << pj; else D.bad |= 1u << pj;
-                if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, pj, any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE));
+                if (lane == 0) sts32(res_addr + (q << 2), 0xFFu | ((any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE) << 24));
             }
-        } else if (cls == 2u) {                            // full GPUs, spec §4
+        } else if (cls == 2u) {                            // full GPUs, spec §4 (several slots: emitted here)
             const uint32_t cj = r0.x;
             if (cj >= D.gpu_min) { if (lane < cj) sink.put(dj + lane, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY)); return; }
             const bool elig = L.valid && !(L.flags & BLOCKED) && L.share == 0;
@@ -773,37 +793,90 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             }
         } else if (cls == 3u) {                            // shared GPU, spec §7
             const uint32_t mj = r0.x;
-            if ((uint64_t)mj >= D.sh_min) { if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT)); return; }
+            if ((uint64_t)mj >= D.sh_min) { if (lane == 0) sts32(res_addr + (q << 2), 0xFFu | (DRA_ST_MEM_LIMIT << 24)); return; }
             const bool elig = L.valid && !(L.flags & BLOCKED) && L.share < 0xFFFFu && L.mem >= mj;
             const uint32_t b = __ballot_sync(FULLMASK, elig);
             const bool win = lane == (uint32_t)__ffs(b) - 1u;
-            if (win) { L.mem -= mj; L.share += 1; sink.put(dj, g0 + lane, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_OK)); }
+            if (win) { L.mem -= mj; L.share += 1; sts32(res_addr + (q << 2), lane); }
             if (b == 0) {
                 D.sh_min = mj;
-                if (lane == 0) sink.put(dj, DRA_GPU_NONE, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT));
+                if (lane == 0) sts32(res_addr + (q << 2), 0xFFu | (DRA_ST_MEM_LIMIT << 24));
             }
-        } else {                                           // co-location run: generic step
+        } else {                                           // co-location run: generic step (emits its own records)
             const uint32_t pj = r0.x;
-            if (pj >= x.k_next) x.k_next = pj + node_step(L, D, lane, g0, x.tbl_ptr, get, pj, cnt, sink, x.have_off);
+            if (pj >= x.k_next) x.k_next = pj + node_step_cold(L, D, lane, g0, x.tbl_ptr, get, pj, cnt, sink, x.have_off);
         }
     };
+    // Common case — every live record of the segment is a plain MIG claim on a homogeneous node: a loop with
+    // no class dispatch and no divergent branch.  Winner = lowest set bit of the ballot (b & -b, no FLO on the
+    // chain), placement bits = sizebits * lowest-candidate-bit (a multiply by a one-hot is the shift).
+    const bool fast = x.homog && __ballot_sync(FULLMASK, live && (is_group || kind != DRA_KIND_MIG)) == 0;
+    if (fast) {
+        const uint32_t lanebit = 1u << lane;
+        auto fstep = [&](const uint4 r0, const uint4 r1, const uint32_t q) {
+            const uint32_t pj = (r1.x >> 16) & 0xFFu;
+            if (((D.bad | D.nocap) >> pj) & 1u) {                          // shape died earlier in this segment: no ballot
+                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | ((((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY) << 24));
+                return;
+            }
+            uint32_t t = ~L.busy & x.gate;
+            t &= t >> r0.x; t &= t >> r0.y; t &= t >> r0.z; t &= t >> r0.w;
+            const uint32_t cand = t & r1.x & 0xFFFFu;
+            const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
+            const uint32_t low = cand & (0u - cand);                       // lowest start, one-hot
+            const bool win = (b & (0u - b)) == lanebit;                    // lowest GPU; b == 0: nobody
+            L.busy |= win ? r1.w * low : 0u;                               // predicated: no divergent branch on the chain
+            sts32_if(win, res_addr + (q << 2), lane | (low << 8));         // start is decoded from `low` in the epilogue
+            if (b == 0) {                                                  // rare: first failure of this shape on the node
+                const bool any = __ballot_sync(FULLMASK, x.mig_offer && (r1.x & 0xFFFFu) != 0) != 0;
+                if (any) D.nocap |= 1u << pj; else D.bad |= 1u << pj;
+                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | ((any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE) << 24));
+            }
+        };
+        uint4 a0 = lds128(x.live_addr), a1 = lds128(x.live_addr + 16), b0, b1;
+        for (uint32_t q = 0; q < nlive; q += 2) {
+            const uint32_t nb_ = x.live_addr + ((q + 1) << 5);
+            if (q + 1 < nlive) { b0 = lds128(nb_); b1 = lds128(nb_ + 16); }
+            fstep(a0, a1, q);
+            if (q + 1 >= nlive) break;
+            if (q + 2 < nlive) { a0 = lds128(nb_ + 32); a1 = lds128(nb_ + 48); }
+            fstep(b0, b1, q + 1);
+        }
+    } else {
     // ping-pong: the next record is in flight while the current one is stepped, no register shuffling
     uint4 a0 = lds128(x.live_addr), a1 = lds128(x.live_addr + 16), b0, b1;
     for (uint32_t q = 0; q < nlive; q += 2) {
         const uint32_t nb_ = x.live_addr + ((q + 1) << 5);
         if (q + 1 < nlive) { b0 = lds128(nb_); b1 = lds128(nb_ + 16); }
-        step(a0, a1);
+        step(a0, a1, q);
         if (q + 1 >= nlive) break;
         if (q + 2 < nlive) { a0 = lds128(nb_ + 32); a1 = lds128(nb_ + 48); }
-        step(b0, b1);
+        step(b0, b1, q + 1);
     }
+    }
+    __syncwarp();
+    long long tq2 = 0; if (x.prof_on) { tq2 = clock64(); x.t_loop += tq2 - tq1; }
+    // epilogue: lane q composes and stores the OutRec of live record q (MIG / SHARED)
+    if (lane < nlive) {
+        const uint4 r1 = lds128(x.live_addr + (lane << 5) + 16);
+        const uint32_t cls = r1.x >> 24;
+        if (cls == 1u || cls == 3u) {
+            const uint32_t res = lds32(res_addr + (lane << 2));
+            const uint32_t w = res & 0xFFu, st_ = res >> 24;
+            const uint32_t prof_ = cls == 1u ? ((r1.x >> 16) & 0xFFu) : (uint32_t)DRA_PROFILE_SHARED;
+            if (w == 0xFFu) sink.put(r1.y, DRA_GPU_NONE, meta(0, 0, prof_, st_));
+            else if (fast) sink.put(r1.y, g0 + w, r1.z | ((uint32_t)__ffs((res >> 8) & 0xFFFFu) - 1u));
+            else sink.put(r1.y, g0 + w, meta((res >> 8) & 0xFFu, (res >> 16) & 0xFFu, prof_, DRA_ST_OK));
+        }
+    }
+    if (x.prof_on) x.t_epi += clock64() - tq2;
     __syncwarp();
 }
 
 // ---- k_pack: node-sorted claims (output of the bucketing kernels), one warp per node -------------------
-// dynamic smem per CTA: [tbl 1024][tbar 16][per warp: inv 512 | ring 2048 | live 1024 | bars 48]
+// dynamic smem per CTA: [tbl 1024][tbar 16][per warp: inv 512 | ring 2048 | live 1024+128 | bars 48]
 constexpr uint32_t PK_TBL = 0, PK_TBAR = 1024, PK_WARP0 = 1040, PK_INV = 0, PK_RING = 512, PK_LIVE = 2560,
-                   PK_BARS = 3584, PK_WSTRIDE = 3632;
+                   PK_BARS = 3712, PK_WSTRIDE = 3760;      // live = 1024 B records + 128 B results
 __host__ __device__ constexpr uint32_t pack_smem_bytes(int wpc) { return PK_WARP0 + (uint32_t)wpc * PK_WSTRIDE; }
 
 // claim m of the node's span from the shared-memory ring (all lanes read one address: broadcast)
@@ -904,15 +977,21 @@ k_pack(const PackArgs a) {
 // warp's matches are in input order) and keep the indices of the claims that select this node; then warp 0
 // packs them.  No sort, no sorted copy, no claim_off: the O(n_node * n_claim) key tests are spread over
 // n_node SMs and every byte after the first CTA's touch comes from L2.
-// dynamic smem: [tbl 1024][bars 16][inv 512][live 1024][counts 64][index lists: n_claim u32, warp w at w*chunk]
-constexpr uint32_t FU_TBL = 0, FU_TBAR = 1024, FU_IBAR = 1032, FU_INV = 1040, FU_LIVE = 1552, FU_CNT = 2576, FU_LIST = 2640;
-__host__ __device__ constexpr size_t fused_smem_bytes(uint32_t n_claim, int nw) {
-    return FU_LIST + ((size_t)((n_claim + nw * 32 - 1) / (nw * 32)) * 32 * nw) * 4 + 16;
+// dynamic smem: [tbl 1024][bars 16][inv 512][live 1024+128][counts 64][index lists: n_claim u32, warp w at w*chunk]
+constexpr uint32_t FU_TBL = 0, FU_TBAR = 1024, FU_IBAR = 1032, FU_INV = 1040, FU_LIVE = 1552, FU_CNT = 2704, FU_LIST = 2832;   // counts: up to 32 warps
+constexpr uint32_t FU_PIECE = 256;          // claims per staged piece (4 KiB bulk copy, own mbarrier)
+constexpr uint32_t FU_MAXPIECE = 8;         // pieces per warp part => staging needs n_claim <= NW * 2048
+__host__ __device__ constexpr size_t fused_list_bytes(uint32_t n_claim, int nw) {
+    return ((size_t)((n_claim + nw * 32 - 1) / (nw * 32)) * 32 * nw) * 4;
+}
+__host__ __device__ constexpr size_t fused_smem_bytes(uint32_t n_claim, int nw, bool stage) {
+    return FU_LIST + (stage ? (size_t)nw * FU_MAXPIECE * 8 : 0) + fused_list_bytes(n_claim, nw) + 16 + (stage ? (size_t)n_claim * 16 + 16 : 0);
 }
 
 template <int NW>
-struct IdxGet {            // claim m of the node from the index lists (generic / co-location path only)
+struct IdxGet {            // claim m of the node, through the index lists
     const uint4* claims; const uint32_t* out_off; uint32_t list_addr, chunk; uint32_t pre[NW];
+    uint32_t stage_addr;   // != 0: the whole claim array is staged in shared memory at this address
     __device__ __forceinline__ uint32_t index_of(uint32_t m) const {
         uint32_t w = 0;
         #pragma unroll
@@ -924,32 +1003,44 @@ struct IdxGet {            // claim m of the node from the index lists (generic 
     }
     __device__ __forceinline__ uint4 operator()(uint32_t m) const {
         const uint32_t i = index_of(m);
-        uint4 c = __ldg(&claims[i]);
+        uint4 c = stage_addr ? lds128(stage_addr + (i << 4)) : __ldg(&claims[i]);
         c.y = out_off ? __ldg(&out_off[i]) : i;
         return c;
     }
 };
 
-template <int NW>
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+#define DRA_STAMP(k) do { if (a.timeline && threadIdx.x == 0) a.timeline[blockIdx.x * 8 + (k)] = (k) == 0 ? globaltimer_ns() : (unsigned long long)clock64(); } while (0)
+
+template <int NW, bool STAGE>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_fused(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
+    DRA_STAMP(0); DRA_STAMP(1);
     const uint32_t sbase = smem_base(dyn_smem);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t node = blockIdx.x;
-    const bool has_node = node < a.n_node;
-    const uint32_t tbar = sbase + FU_TBAR, ibar = sbase + FU_IBAR, list_addr = sbase + FU_LIST;
+    const bool has_node = node < a.n_node;       // the extra CTA (blockIdx == n_node) handles claims that name no node
+    const uint32_t tbar = sbase + FU_TBAR, ibar = sbase + FU_IBAR;
+    const uint32_t list_addr = sbase + FU_LIST + (STAGE ? (uint32_t)NW * FU_MAXPIECE * 8u : 0u);
+    const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(a.n_claim, NW) + 15u) & ~15u) : 0u;
+    const uint32_t sbar = sbase + FU_LIST;       // STAGE: NW x FU_MAXPIECE piece barriers
 
     // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
     uint32_t g0 = 0, g1 = 0;
     if (has_node) { g0 = __ldg(&a.node_off[node]); g1 = __ldg(&a.node_off[node + 1]); }
     if (threadIdx.x == 0) {
         mbar_init_a(tbar, 1); mbar_init_a(ibar, 1);
+        if (STAGE) for (uint32_t q = 0; q < NW * FU_MAXPIECE; ++q) mbar_init_a(sbar + q * 8, 1);
         mbar_fence_init();
         tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
     }
     const uint32_t ng = g1 - g0;
     if (threadIdx.x == 0 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
+    if (STAGE) __syncthreads();                    // piece barriers are initialised before any warp arms them
+    DRA_STAMP(2);
 
     // ---- filter: which claims select this node (all warps) ------------------------------------------
     const uint32_t chunk = ((a.n_claim + NW * 32 - 1) / (NW * 32)) * 32;      // per-warp part, multiple of 32
@@ -958,49 +1049,75 @@ k_fused(const PackArgs a) {
     const uint32_t my_list = list_addr + (lo << 2);
     const uint32_t want = has_node ? node : 0xFFFFFFFEu;
     uint32_t cntw = 0;
-    constexpr int U = 8;
-    const uint32_t* keyp = reinterpret_cast<const uint32_t*>(a.claims) + 1;      // .y of claim i at keyp[4*i]
-    uint32_t key[U], nxt[U];
-    #pragma unroll
-    for (int u = 0; u < U; ++u) { const uint32_t i = lo + u * 32 + lane; key[u] = i < hi ? __ldg(keyp + 4 * (size_t)i) : 0xFFFFFFFFu; }
-    for (uint32_t base = lo; base < hi; base += 32 * U) {
-        #pragma unroll
-        for (int u = 0; u < U; ++u) {                      // next batch goes out before this one is looked at
-            const uint32_t i = base + 32 * U + u * 32 + lane;
-            nxt[u] = i < hi ? __ldg(keyp + 4 * (size_t)i) : 0xFFFFFFFFu;
+    if (!has_node) {
+        // claims that name no node of the inventory: INVALID (spec §3); no state is touched
+        for (uint32_t i = threadIdx.x; i < a.n_claim; i += NW * 32) {
+            const uint4 c = __ldg(&a.claims[i]);
+            if (c.y < a.n_node) continue;
+            const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
+            const uint32_t kind = c.x & 0xFFu;
+            const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
+            if (dst < a.n_out) {
+                const uint2 r_ = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+                a.out[dst] = r_;
+                for (uint32_t p = 0; p < a.peer.world; ++p) if (p != a.peer.rank) a.peer.peer_out[p][dst] = r_;
+            } else a.err.set(ERR_OUT_RANGE);
         }
-        #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t i = base + u * 32 + lane;
-            const bool m = key[u] == want;
-            const uint32_t b = __ballot_sync(FULLMASK, m);
-            if (b) {
-                if (m) sts32(my_list + ((cntw + (uint32_t)__popc(b & ltmask)) << 2), i);
-                cntw += (uint32_t)__popc(b);
-            }
-            if (node == 0) {                       // claims that name no node: INVALID, written by CTA 0 (spec §3)
-                const bool none = i < hi && key[u] >= a.n_node;
-                if (__any_sync(FULLMASK, none) && none) {
-                    const uint4 c = __ldg(&a.claims[i]);
-                    const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
-                    const uint32_t kind = c.x & 0xFFu;
-                    const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
-                    if (dst < a.n_out) {
-                        const uint2 r_ = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
-                        a.out[dst] = r_;
-                        for (uint32_t p = 0; p < a.peer.world; ++p) if (p != a.peer.rank) a.peer.peer_out[p][dst] = r_;
-                    } else a.err.set(ERR_OUT_RANGE);
-                }
-            }
-        }
-        #pragma unroll
-        for (int u = 0; u < U; ++u) key[u] = nxt[u];
     }
+    auto scan = [&](const uint32_t i, const uint32_t keyv) {          // one claim per lane; warp-uniform control flow
+        const bool m = has_node && keyv == want;
+        const uint32_t b = __ballot_sync(FULLMASK, m);
+        if (b) {
+            if (m) sts32(my_list + ((cntw + (uint32_t)__popc(b & ltmask)) << 2), i);
+            cntw += (uint32_t)__popc(b);
+        }
+    };
+    constexpr int U = 8;
+    if (STAGE) {
+        // the warp's whole part goes out as 4 KiB TMA bulk copies, all in flight at once; pieces are scanned
+        // from shared memory as they land, and the pack phase later reads the claims from the same copy
+        const uint32_t npiece = hi > lo ? (hi - lo + FU_PIECE - 1) / FU_PIECE : 0;
+        if (lane == 0)
+            for (uint32_t q = 0; q < npiece; ++q) {
+                const uint32_t c0 = lo + q * FU_PIECE, n = min(FU_PIECE, hi - c0);
+                tma_load_a(stage_addr + (c0 << 4), a.claims + c0, n * 16u, sbar + (wid * FU_MAXPIECE + q) * 8);
+            }
+        for (uint32_t q = 0; q < npiece; ++q) {
+            mbar_wait_a(sbar + (wid * FU_MAXPIECE + q) * 8, 0);
+            uint32_t kv[U];
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {                      // all 8 shared loads in flight before the first test
+                const uint32_t i = lo + q * FU_PIECE + u * 32 + lane;
+                kv[u] = i < hi ? lds32(stage_addr + (i << 4) + 4) : 0xFFFFFFFFu;
+            }
+            #pragma unroll
+            for (int u = 0; u < U; ++u) scan(lo + q * FU_PIECE + u * 32 + lane, kv[u]);
+        }
+    } else {
+        const uint32_t* keyp = reinterpret_cast<const uint32_t*>(a.claims) + 1;      // .y of claim i at keyp[4*i]
+        uint32_t key[U], nxt[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) { const uint32_t i = lo + u * 32 + lane; key[u] = i < hi ? __ldg(keyp + 4 * (size_t)i) : 0xFFFFFFFFu; }
+        for (uint32_t base = lo; base < hi; base += 32 * U) {
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {                      // next batch goes out before this one is looked at
+                const uint32_t i = base + 32 * U + u * 32 + lane;
+                nxt[u] = i < hi ? __ldg(keyp + 4 * (size_t)i) : 0xFFFFFFFFu;
+            }
+            #pragma unroll
+            for (int u = 0; u < U; ++u) scan(base + u * 32 + lane, key[u]);
+            #pragma unroll
+            for (int u = 0; u < U; ++u) key[u] = nxt[u];
+        }
+    }
+    DRA_STAMP(3);
     if (lane == 0) sts32(sbase + FU_CNT + (wid << 2), cntw);
     __syncthreads();
+    DRA_STAMP(4);
 
     IdxGet<NW> get;
     get.claims = a.claims; get.out_off = a.out_off; get.list_addr = list_addr; get.chunk = chunk;
+    get.stage_addr = stage_addr;
     uint32_t cnt = 0;
     #pragma unroll
     for (int i = 0; i < NW; ++i) { get.pre[i] = cnt; cnt += lds32(sbase + FU_CNT + (i << 2)); }
@@ -1031,6 +1148,8 @@ k_fused(const PackArgs a) {
             uint4 rec = make_uint4(0, 0, 0, 0);
             if (ng) { mbar_wait_a(ibar, 0); if (lane < ng) rec = lds128(sbase + FU_INV + lane * 16); }
             x.begin(rec, lane < ng);
+            x.prof_on = a.timeline != nullptr;
+            DRA_STAMP(5);
 
             const uint32_t nseg = (cnt + SEG - 1) / SEG;
             for (uint32_t seg = 0; seg < nseg; ++seg) {
@@ -1040,6 +1159,11 @@ k_fused(const PackArgs a) {
                 c_cur = c_nxt; p_cur = p_nxt;
             }
             if (lane < ng) a.inv_dst[g0 + lane] = x.L.store(rec);
+            DRA_STAMP(6);
+            if (a.timeline && lane == 0) {
+                a.timeline[blockIdx.x * 8 + 7] = cnt | ((unsigned long long)x.n_live << 32);
+                a.timeline[blockIdx.x * 8 + 0] = (unsigned long long)x.t_pre | ((unsigned long long)x.t_loop << 20) | ((unsigned long long)x.t_epi << 40);
+            }
         }
     }
     if (a.peer.world == 0) return;
@@ -1051,7 +1175,7 @@ k_fused(const PackArgs a) {
     if (has_node) {
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
-            const uint4 c = __ldg(&a.claims[i]);
+            const uint4 c = STAGE ? lds128(stage_addr + (i << 4)) : __ldg(&a.claims[i]);
             const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
             const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
             const uint32_t slots = (kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
