@@ -815,22 +815,25 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
         const uint32_t lanebit = 1u << lane;
         auto fstep = [&](const uint4 r0, const uint4 r1, const uint32_t q) {
             const uint32_t pj = (r1.x >> 16) & 0xFFu;
-            if (((D.bad | D.nocap) >> pj) & 1u) {                          // shape died earlier in this segment: no ballot
-                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | ((((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY) << 24));
-                return;
-            }
+            const uint32_t deadm = D.bad | D.nocap;
             uint32_t t = ~L.busy & x.gate;
             t &= t >> r0.x; t &= t >> r0.y; t &= t >> r0.z; t &= t >> r0.w;
-            const uint32_t cand = t & r1.x & 0xFFFFu;
+            uint32_t cand = t & r1.x & 0xFFFFu;
+            cand = ((deadm >> pj) & 1u) ? 0u : cand;                       // a shape that died earlier: nobody bids (no branch)
             const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
             const uint32_t low = cand & (0u - cand);                       // lowest start, one-hot
             const bool win = (b & (0u - b)) == lanebit;                    // lowest GPU; b == 0: nobody
             L.busy |= win ? r1.w * low : 0u;                               // predicated: no divergent branch on the chain
             sts32_if(win, res_addr + (q << 2), lane | (low << 8));         // start is decoded from `low` in the epilogue
-            if (b == 0) {                                                  // rare: first failure of this shape on the node
-                const bool any = __ballot_sync(FULLMASK, x.mig_offer && (r1.x & 0xFFFFu) != 0) != 0;
-                if (any) D.nocap |= 1u << pj; else D.bad |= 1u << pj;
-                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | ((any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE) << 24));
+            if (b == 0) {                                                  // rare: the shape fails (now, or already dead)
+                uint32_t stt;
+                if ((deadm >> pj) & 1u) stt = ((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY;
+                else {
+                    const bool any = __ballot_sync(FULLMASK, x.mig_offer && (r1.x & 0xFFFFu) != 0) != 0;
+                    if (any) D.nocap |= 1u << pj; else D.bad |= 1u << pj;
+                    stt = any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE;
+                }
+                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | (stt << 24));
             }
         };
         uint4 a0 = lds128(x.live_addr), a1 = lds128(x.live_addr + 16), b0, b1;
