@@ -103,6 +103,7 @@ struct dra_ctx {
     cudaEvent_t ev[8] = {};
     bool ev_ok = false;
     float timings[5] = {0, 0, 0, 0, 0};
+    uint32_t ev_mask = 0;
     int hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0, fused_smem_set_stage = 0;
     uint64_t fused_max_work = 6000000ull;   // n_node * n_claim up to which the single-launch kernel is used
 
@@ -203,10 +204,12 @@ int upload_table(dra_ctx* ctx) {
     return DRA_OK;
 }
 
-struct Prof {
+struct Prof {          // event i brackets stage i: [hist, scan, scatter, pack/fused, all-gather]
     dra_ctx* c; int i = 0;
-    explicit Prof(dra_ctx* ctx) : c(ctx) { if (c->profiling) cudaEventRecord(c->ev[0], c->stream); }
-    void mark() { if (c->profiling) cudaEventRecord(c->ev[++i], c->stream); }
+    explicit Prof(dra_ctx* ctx) : c(ctx) { c->ev_mask = 0; rec(0); }
+    void rec(int k) { if (c->profiling) { cudaEventRecord(c->ev[k], c->stream); c->ev_mask |= 1u << k; } i = k; }
+    void mark() { rec(i + 1); }
+    void skip_to(int k) { rec(k); }      // stages before k did not run in this call
 };
 
 // The kernel chain of one Allocate batch on device-resident inputs.  Enqueues only.
@@ -254,7 +257,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
             CU(cudaMemsetAsync(ctx->d_timeline, 0, ctx->tl_cap * 8, ctx->stream));
             a.timeline = ctx->d_timeline; ctx->tl_n = (n_node + 1) * 8;
         }
-        prof.mark(); prof.mark(); prof.mark();
+        prof.skip_to(3);
         // grid = one CTA per node + one CTA for the claims that name no node
         if (stage) k_fused<FUSED_NW, true><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
         else k_fused<FUSED_NW, false><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
@@ -270,7 +273,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         k_sorted_prep<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
                                                        ctx->d_sorted, d_out, n_out, err);
         ctx->launches += 1;
-        prof.mark(); prof.mark(); prof.mark();
+        prof.mark(); prof.skip_to(3);
     } else {
         const size_t nbp = ((size_t)n_node + 2) & ~(size_t)1;
         const size_t small_smem = nbp * 4 + 32 * nbp * 2 + (size_t)n_claim * 2 + 16;
@@ -288,7 +291,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
             k_bucket_small<<<1, 1024, small_smem, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
                                                                  ctx->d_sorted, d_out, n_out, err, pf);
             ctx->launches += 1;
-            prof.mark(); prof.mark(); prof.mark();
+            prof.mark(); prof.skip_to(3);
         } else {
             Tiling t = tiling(n_claim);
             size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
@@ -327,6 +330,7 @@ int collect_timings(dra_ctx* ctx, int n_marks) {
     for (int i = 0; i < 5; ++i) ctx->timings[i] = 0.f;
     for (int i = 0; i < n_marks && i < 5; ++i) {
         float ms = 0.f;
+        if (!((ctx->ev_mask >> i) & 1u) || !((ctx->ev_mask >> (i + 1)) & 1u)) continue;
         if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->timings[i] = ms * 1000.f;
     }
     (void)cudaGetLastError();   // an event that was never recorded is not an error of the batch
@@ -735,7 +739,7 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
         } else if (d_out_all) {                             // caller wants its own copy: one D2D copy node
             CU(cudaMemcpyAsync(d_out_all, table, (size_t)ctx->world * n_per * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         }
-        if (ctx->profiling) cudaEventRecord(ctx->ev[5], ctx->stream);
+        if (ctx->profiling && !tail_done) { cudaEventRecord(ctx->ev[5], ctx->stream); ctx->ev_mask |= 1u << 5; }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "peer all-gather launch: %s", cudaGetErrorString(e));
         return DRA_OK;
@@ -750,7 +754,7 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     // the one collective of the path: every rank's OutRec slice to every rank (in place), same stream
     ncclResult_t r = g_nccl.AllGather(mine, d_out_all, (size_t)n_per_rank * 8, ncclUint8, ctx->comm, ctx->stream);
     if (r != ncclSuccess) return fail(ctx, DRA_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-    if (ctx->profiling) cudaEventRecord(ctx->ev[5], ctx->stream);
+    if (ctx->profiling) { cudaEventRecord(ctx->ev[5], ctx->stream); ctx->ev_mask |= 1u << 5; }
     return DRA_OK;
 }
 
