@@ -811,8 +811,33 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     // no class dispatch and no divergent branch.  Winner = lowest set bit of the ballot (b & -b, no FLO on the
     // chain), placement bits = sizebits * lowest-candidate-bit (a multiply by a one-hot is the shift).
     const bool fast = x.homog && __ballot_sync(FULLMASK, live && (is_group || kind != DRA_KIND_MIG)) == 0;
-    if (fast) {
-        const uint32_t lanebit = 1u << lane;
+    const bool fast_sh = !fast && __ballot_sync(FULLMASK, live && kind != DRA_KIND_SHARED) == 0;
+    const uint32_t lanebit = 1u << lane;
+    if (fast_sh) {
+        // every live record is a SHARED claim (spec §7): flags cannot change inside the segment
+        const bool share_ok = L.valid && !(L.flags & BLOCKED);
+        auto sstep = [&](const uint4 r0, const uint32_t q) {
+            const uint32_t mj = r0.x;
+            const bool elig = share_ok && L.share < 0xFFFFu && L.mem >= mj && (uint64_t)mj < D.sh_min;
+            const uint32_t b = __ballot_sync(FULLMASK, elig);
+            const bool win = (b & (0u - b)) == lanebit;                    // lowest GPU; b == 0: nobody
+            L.mem -= win ? mj : 0u; L.share += win ? 1u : 0u;
+            sts32_if(win, res_addr + (q << 2), lane);
+            if (b == 0) {
+                if ((uint64_t)mj < D.sh_min) D.sh_min = mj;
+                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | (DRA_ST_MEM_LIMIT << 24));
+            }
+        };
+        uint4 a0 = lds128(x.live_addr), b0;
+        for (uint32_t q = 0; q < nlive; q += 2) {
+            const uint32_t nb_ = x.live_addr + ((q + 1) << 5);
+            if (q + 1 < nlive) b0 = lds128(nb_);
+            sstep(a0, q);
+            if (q + 1 >= nlive) break;
+            if (q + 2 < nlive) a0 = lds128(nb_ + 32);
+            sstep(b0, q + 1);
+        }
+    } else if (fast) {
         auto fstep = [&](const uint4 r0, const uint4 r1, const uint32_t q) {
             const uint32_t pj = (r1.x >> 16) & 0xFFu;
             const uint32_t deadm = D.bad | D.nocap;
