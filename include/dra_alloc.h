@@ -104,6 +104,48 @@ typedef struct dra_profile_tbl {
     dra_prof_ent ent[DRA_MAX_PROFILES];
 } dra_profile_tbl;
 
+/* Per-GPU attributes a selector can test — the attributes GpuInfo.GetDevice publishes
+ * (cmd/nvidia-dra-plugin/deviceinfo.go:102-132), interned to integers by the host.  spec §10. */
+typedef struct dra_gpu_attr {
+    uint32_t mem_total_mib;
+    uint32_t cc;            /* cudaComputeCapability: major << 8 | minor */
+    uint32_t index;
+    uint16_t product;       /* host-interned productName id */
+    uint16_t driver_major;
+} dra_gpu_attr;
+
+/* One instruction of a selector program (postfix, boolean stack).  Flat form of the legacy
+ * GpuClaimParameters.spec.selector trees (demo/specs/selectors/parameters.yaml:7-27) and of the CEL subset
+ * in demo/specs/quickstart/gpu-test6.yaml:23-31. */
+typedef struct dra_sel_ins {
+    uint8_t  op;            /* DRA_SEL_* */
+    uint8_t  attr;          /* DRA_ATTR_* */
+    uint8_t  cmp;           /* DRA_CMP_* */
+    uint8_t  rsvd;
+    uint32_t value;
+} dra_sel_ins;
+
+#define DRA_SEL_MAX_INS 8u
+typedef struct dra_selector { dra_sel_ins ins[DRA_SEL_MAX_INS]; } dra_selector;
+
+#define DRA_SEL_END 0u
+#define DRA_SEL_CMP 1u
+#define DRA_SEL_AND 2u
+#define DRA_SEL_OR  3u
+#define DRA_SEL_NOT 4u
+#define DRA_ATTR_MEMORY_MIB   0u
+#define DRA_ATTR_CC           1u
+#define DRA_ATTR_INDEX        2u
+#define DRA_ATTR_PRODUCT      3u
+#define DRA_ATTR_DRIVER_MAJOR 4u
+#define DRA_CMP_EQ 0u
+#define DRA_CMP_NE 1u
+#define DRA_CMP_LT 2u
+#define DRA_CMP_LE 3u
+#define DRA_CMP_GT 4u
+#define DRA_CMP_GE 5u
+#define DRA_CMP_IN_MASK 6u
+
 /* ---- context ------------------------------------------------------------------------------------- */
 
 typedef struct dra_ctx dra_ctx;
@@ -150,6 +192,10 @@ int  dra_set_placement_table(dra_ctx* ctx, uint32_t model, const dra_profile_tbl
  * the classic driver.  gpus sorted by (node, local index); node_off has n_node+1 entries. Copied. */
 int  dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu,
                        const uint32_t* node_off, uint32_t n_node);
+/* Optional, spec §10: attributes of the same n_gpu GPUs (same order) and the selector table.  A claim names
+ * its selector by 1-based id: kinds GPU and MIG in mem_limit_mib, kind SHARED in group. */
+int  dra_set_gpu_attrs(dra_ctx* ctx, const dra_gpu_attr* attrs, uint32_t n_gpu);
+int  dra_set_selectors(dra_ctx* ctx, const dra_selector* sels, uint32_t n_sel);
 /* Read the live inventory back (n_gpu records). */
 int  dra_get_inventory(dra_ctx* ctx, dra_gpu_rec* gpus, uint32_t n_gpu);
 /* Restore the live inventory to what dra_set_inventory last loaded (device-side copy). */

@@ -39,6 +39,8 @@ SYMBOLS = {
     "dra_last_error": (C.c_char_p, [_vp]),
     "dra_set_placement_table": (_i32, [_vp, _u32, _vp]),
     "dra_set_inventory": (_i32, [_vp, _vp, _u32, _vp, _u32]),
+    "dra_set_gpu_attrs": (_i32, [_vp, _vp, _u32]),
+    "dra_set_selectors": (_i32, [_vp, _vp, _u32]),
     "dra_get_inventory": (_i32, [_vp, _vp, _u32]),
     "dra_reset_inventory": (_i32, [_vp]),
     "dra_allocate_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32]),
@@ -174,6 +176,20 @@ class Context:
         off = np.ascontiguousarray(node_off, dtype=np.uint32)
         self._check(self._lib.dra_set_inventory(self._h, _ptr(g), len(g), _ptr(off), len(off) - 1))
         self.n_gpu, self.n_node = len(g), len(off) - 1
+
+    def set_gpu_attrs(self, attrs: np.ndarray | None):
+        if attrs is None or len(attrs) == 0:
+            self._check(self._lib.dra_set_gpu_attrs(self._h, None, 0))
+            return
+        a = np.ascontiguousarray(attrs, dtype=R.ATTR_DTYPE)
+        self._check(self._lib.dra_set_gpu_attrs(self._h, _ptr(a), len(a)))
+
+    def set_selectors(self, sels: np.ndarray | None):
+        if sels is None or len(sels) == 0:
+            self._check(self._lib.dra_set_selectors(self._h, None, 0))
+            return
+        s_ = np.ascontiguousarray(sels, dtype=R.SEL_INS_DTYPE).reshape(-1, R.SEL_MAX_INS)
+        self._check(self._lib.dra_set_selectors(self._h, _ptr(s_), len(s_)))
 
     def get_inventory(self) -> np.ndarray:
         g = np.zeros(self.n_gpu, dtype=R.GPU_DTYPE)

@@ -77,6 +77,8 @@ struct dra_ctx {
     uint32_t* d_tbl = nullptr;
     dra_profile_tbl h_tbl[DRA_MAX_MODELS];
     bool tbl_dirty = true;
+    uint4* d_attrs = nullptr;  uint32_t n_attr = 0;      // spec §10
+    uint4* d_sels = nullptr;   uint32_t n_sel = 0;
 
     // batch buffers (device)
     size_t cap_claims = 0, cap_out = 0, cap_hist = 0, cap_nodes = 0, cap_pairs = 0, cap_pods = 0;
@@ -194,6 +196,8 @@ int ensure_batch(dra_ctx* ctx, uint32_t n_claim, uint32_t n_out, bool own_io) {
     return rc;
 }
 
+SelCtx sel_of(dra_ctx* ctx) { return SelCtx{ctx->n_attr == ctx->n_gpu ? ctx->d_attrs : nullptr, ctx->d_sels, ctx->n_sel}; }
+
 Err err_of(dra_ctx* ctx) { return Err{ctx->d_err, (volatile uint32_t*)ctx->h_err_dev}; }
 
 int upload_table(dra_ctx* ctx) {
@@ -230,6 +234,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     a.tbl = ctx->d_tbl;
     a.out = d_out; a.n_out = n_out; a.n_node = n_node; a.have_off = d_out_off != nullptr;
     a.err = err;
+    a.sel = sel_of(ctx);
 
     // Small batches: ONE launch.  Every node's CTA filters the claim stream for itself (n_node * n_claim key
     // tests spread over n_node SMs, data from L2) and packs — no sort, no sorted copy.
@@ -405,7 +410,7 @@ void dra_ctx_destroy(dra_ctx* c) {
     if (c->d_ticket) cudaFree(c->d_ticket);
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
-                   c->d_pair_pod, c->d_bits, c->d_err};
+                   c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels};
     for (void* p : dev) if (p) cudaFree(p);
     if (c->h_err) cudaFreeHost((void*)c->h_err);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -463,6 +468,33 @@ int dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu, con
     ctx->n_gpu = n_gpu; ctx->n_node = n_node;
     ctx->cap_hist = 0;  // histogram geometry depends on n_node
     if (ctx->d_hist) { CU(cudaFree(ctx->d_hist)); ctx->d_hist = nullptr; }
+    return DRA_OK;
+}
+
+int dra_set_gpu_attrs(dra_ctx* ctx, const dra_gpu_attr* attrs, uint32_t n_gpu) {
+    if (!ctx || (n_gpu && !attrs)) return DRA_E_INVAL;
+    static_assert(sizeof(dra_gpu_attr) == 16 && sizeof(dra_selector) == 64, "selector record layout");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_attrs) { CU(cudaFree(ctx->d_attrs)); ctx->d_attrs = nullptr; }
+    ctx->n_attr = 0;
+    if (!n_gpu) return DRA_OK;
+    CU(cudaMalloc((void**)&ctx->d_attrs, (size_t)n_gpu * 16 + 64));
+    CU(cudaMemcpy(ctx->d_attrs, attrs, (size_t)n_gpu * 16, cudaMemcpyHostToDevice));
+    ctx->n_attr = n_gpu;
+    return DRA_OK;
+}
+
+int dra_set_selectors(dra_ctx* ctx, const dra_selector* sels, uint32_t n_sel) {
+    if (!ctx || (n_sel && !sels)) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_sels) { CU(cudaFree(ctx->d_sels)); ctx->d_sels = nullptr; }
+    ctx->n_sel = 0;
+    if (!n_sel) return DRA_OK;
+    CU(cudaMalloc((void**)&ctx->d_sels, (size_t)n_sel * 64 + 64));
+    CU(cudaMemcpy(ctx->d_sels, sels, (size_t)n_sel * 64, cudaMemcpyHostToDevice));
+    ctx->n_sel = n_sel;
     return DRA_OK;
 }
 
@@ -583,6 +615,7 @@ int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
         a.claims = ctx->d_claims; a.pod_off = ctx->d_pod_off; a.n_pod = n_pod;
         a.cand_nodes = ctx->d_cand_nodes; a.cand_off = ctx->d_cand_off; a.pair_pod = ctx->d_pair_pod; a.n_pair = n_pair;
         a.inv = ctx->d_inv_live; a.node_off = ctx->d_node_off; a.n_node = ctx->n_node; a.tbl = ctx->d_tbl; a.bits = ctx->d_bits;
+        a.sel = sel_of(ctx);
         Prof prof(ctx);
         uint32_t grid = std::min((n_pair + 7) / 8, 148u * 8u);
         k_unsuitable<8><<<grid, 256, 0, ctx->stream>>>(a);

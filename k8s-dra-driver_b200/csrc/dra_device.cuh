@@ -165,6 +165,57 @@ struct FlagSink {
     __device__ __forceinline__ bool stop() const { return failed; }
 };
 
+// ---- selectors (spec §10) ----------------------------------------------------------------------------
+// GpuAttr as uint4: x memTotalMiB, y cc, z index, w product | driverMajor<<16.  Selector = 4 x uint4 (8 SelIns).
+struct SelCtx { const uint4* attrs; const uint4* sels; uint32_t n_sel; };
+
+__device__ __forceinline__ uint32_t claim_sel(uint32_t kind, uint32_t mem, uint32_t group) {
+    return (kind == DRA_KIND_GPU || kind == DRA_KIND_MIG) ? mem : (kind == DRA_KIND_SHARED ? group : 0u);
+}
+
+// does GPU `gidx` pass selector `id`?  Postfix program over a boolean stack kept in a bit register.
+__device__ __noinline__ bool sel_pass(const SelCtx sc, uint32_t id, uint32_t gidx, bool valid) {
+    if (id == 0) return true;
+    if (id > sc.n_sel || !valid) return false;
+    uint4 a = make_uint4(0, 0, 0, 0);
+    if (sc.attrs) a = __ldg(&sc.attrs[gidx]);
+    uint32_t stack = 0, sp = 0; bool any = false, bad = false;
+    #pragma unroll 1
+    for (uint32_t q = 0; q < 4 && !bad; ++q) {
+        const uint4 w = __ldg(&sc.sels[(size_t)(id - 1) * 4 + q]);
+        const uint32_t hdr[2] = {w.x, w.z}, val[2] = {w.y, w.w};
+        #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t op = hdr[h] & 0xFFu, attr = (hdr[h] >> 8) & 0xFFu, cmp = (hdr[h] >> 16) & 0xFFu, v2 = val[h];
+            if (op == DRA_SEL_END) { q = 4; break; }
+            any = true;
+            if (op == DRA_SEL_CMP) {
+                uint32_t v = 0;
+                if (attr == DRA_ATTR_MEMORY_MIB) v = a.x; else if (attr == DRA_ATTR_CC) v = a.y;
+                else if (attr == DRA_ATTR_INDEX) v = a.z; else if (attr == DRA_ATTR_PRODUCT) v = a.w & 0xFFFFu;
+                else if (attr == DRA_ATTR_DRIVER_MAJOR) v = a.w >> 16; else { bad = true; break; }
+                bool r = false;
+                if (cmp == DRA_CMP_EQ) r = v == v2; else if (cmp == DRA_CMP_NE) r = v != v2;
+                else if (cmp == DRA_CMP_LT) r = v < v2; else if (cmp == DRA_CMP_LE) r = v <= v2;
+                else if (cmp == DRA_CMP_GT) r = v > v2; else if (cmp == DRA_CMP_GE) r = v >= v2;
+                else if (cmp == DRA_CMP_IN_MASK) r = v < 32u && ((v2 >> v) & 1u); else { bad = true; break; }
+                stack |= (r ? 1u : 0u) << sp; ++sp;
+            } else if (op == DRA_SEL_AND || op == DRA_SEL_OR) {
+                if (sp < 2) { bad = true; break; }
+                const uint32_t b_ = (stack >> (sp - 1)) & 1u, a_ = (stack >> (sp - 2)) & 1u;
+                sp -= 2; stack &= (1u << sp) - 1u;
+                stack |= (op == DRA_SEL_AND ? (a_ & b_) : (a_ | b_)) << sp; ++sp;
+            } else if (op == DRA_SEL_NOT) {
+                if (sp < 1) { bad = true; break; }
+                stack ^= 1u << (sp - 1);
+            } else { bad = true; break; }
+        }
+    }
+    if (bad) return false;
+    if (!any) return true;
+    return sp >= 1 && ((stack >> (sp - 1)) & 1u);
+}
+
 __device__ __forceinline__ bool claim_invalid(uint32_t kind, uint32_t prof, uint32_t count, bool have_off) {
     if (kind > DRA_KIND_SHARED) return true;
     if (kind == DRA_KIND_GPU) return count == 0 || count > DRA_MAX_COUNT || (!have_off && count != 1);
@@ -177,30 +228,36 @@ __device__ __forceinline__ bool claim_invalid(uint32_t kind, uint32_t prof, uint
 template <class Get, class Sink>
 __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, uint32_t g0,
                                               const uint32_t* __restrict__ tbl_s, Get get, uint32_t k,
-                                              uint32_t cnt, Sink& sink, bool have_off) {
+                                              uint32_t cnt, Sink& sink, bool have_off, const SelCtx sc) {
     const uint4 c = get(k);
     const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
-    const uint32_t dst = c.y, mem = c.z, group = c.w;
+    const uint32_t dst = c.y, group = c.w;
     constexpr uint32_t BLOCKED = DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE;
+    const uint32_t sel = claim_sel(kind, c.z, c.w);
+    const uint32_t mem = kind == DRA_KIND_SHARED ? c.z : 0u;
+    // a claim with a selector sees its own subset of GPUs: the node-wide failure memo does not apply to it
+    const bool memo = sel == 0;
+    const bool selok = sel == 0 ? true : sel_pass(sc, sel, g0 + lane, L.valid);
 
-    if (claim_invalid(kind, prof, count, have_off)) {               // spec §3
+    if (claim_invalid(kind, prof, count, have_off) || sel > sc.n_sel) {   // spec §3, §10
         const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU
                           : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : prof;
-        if (sink.range(dst, 1)) sink.fail(dst, 1, op, DRA_ST_INVALID);
+        const uint32_t sl = (kind == DRA_KIND_GPU && !claim_invalid(kind, prof, count, have_off)) ? count : 1u;
+        if (sink.range(dst, sl)) sink.fail(dst, sl, op, DRA_ST_INVALID);
         return 1;
     }
 
     if (kind == DRA_KIND_MIG && group == 0) {                       // spec §5
         if (!sink.range(dst, 1)) return 1;
         const uint32_t pbit = 1u << prof;
-        if ((D.bad | D.nocap) & pbit) {
+        if (memo && ((D.bad | D.nocap) & pbit)) {
             sink.fail(dst, 1, prof, (D.bad & pbit) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY);
             return 1;
         }
         const uint32_t e = tbl_s[L.model * DRA_MAX_PROFILES + prof];
         const uint32_t smask = e >> 16, size = e & 0xFFu;
         const bool offers = L.valid && (L.flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_UNAVAILABLE)) == DRA_GPU_MIG_ENABLED
-                            && smask != 0;
+                            && smask != 0 && selok;
         const bool elig = offers && !(L.flags & DRA_GPU_FULL_ALLOCATED);
         const uint32_t cand = elig ? (fit_map(~L.busy & 0xFFFFu, size) & smask) : 0u;
         const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
@@ -212,7 +269,7 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
             }
         } else {
             const bool any = __ballot_sync(FULLMASK, offers) != 0;
-            if (any) D.nocap |= pbit; else D.bad |= pbit;
+            if (memo) { if (any) D.nocap |= pbit; else D.bad |= pbit; }
             sink.fail(dst, 1, prof, any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE);
         }
         return 1;
@@ -224,12 +281,12 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
         while (e_ < lim) {
             const uint4 cm = get(e_);
             const uint32_t km = cm.x & 0xFFu, pm = (cm.x >> 8) & 0xFFu;
-            if (km != DRA_KIND_MIG || cm.w != group || pm >= DRA_MAX_PROFILES) break;
+            if (km != DRA_KIND_MIG || cm.w != group || pm >= DRA_MAX_PROFILES || cm.z > sc.n_sel) break;
             ++e_;
         }
         // every lane tries the whole run on a private copy of its own GPU
         uint32_t tb = L.busy;
-        bool ok = L.valid && (L.flags & BLOCKED) == DRA_GPU_MIG_ENABLED;
+        bool ok = L.valid && (L.flags & BLOCKED) == DRA_GPU_MIG_ENABLED && selok;     // the first member's selector
         for (uint32_t m = k; m < e_; ++m) {
             const uint32_t pm = (get(m).x >> 8) & 0xFFu;
             const uint32_t en = tbl_s[L.model * DRA_MAX_PROFILES + pm];
@@ -268,8 +325,8 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
 
     if (kind == DRA_KIND_GPU) {                                     // spec §4
         if (!sink.range(dst, count)) return 1;
-        if (count >= D.gpu_min) { sink.fail(dst, count, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY); return 1; }
-        const bool elig = L.valid && !(L.flags & BLOCKED) && L.share == 0;
+        if (memo && count >= D.gpu_min) { sink.fail(dst, count, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY); return 1; }
+        const bool elig = L.valid && !(L.flags & BLOCKED) && L.share == 0 && selok;
         const uint32_t b = __ballot_sync(FULLMASK, elig);
         if ((uint32_t)__popc(b) >= count) {
             const uint32_t r = (uint32_t)__popc(b & lanemask_lt());
@@ -278,7 +335,7 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
                 sink.put(dst + r, g0 + lane, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_OK));
             }
         } else {
-            D.gpu_min = count;
+            if (memo) D.gpu_min = count;
             sink.fail(dst, count, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY);
         }
         return 1;
@@ -286,9 +343,9 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
 
     // SHARED, spec §7
     if (!sink.range(dst, 1)) return 1;
-    if ((uint64_t)mem >= D.sh_min) { sink.fail(dst, 1, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT); return 1; }
+    if (memo && (uint64_t)mem >= D.sh_min) { sink.fail(dst, 1, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT); return 1; }
     {
-        const bool elig = L.valid && !(L.flags & BLOCKED) && L.share < 0xFFFFu && L.mem >= mem;
+        const bool elig = L.valid && !(L.flags & BLOCKED) && L.share < 0xFFFFu && L.mem >= mem && selok;
         const uint32_t b = __ballot_sync(FULLMASK, elig);
         if (b) {
             if (lane == (uint32_t)__ffs(b) - 1u) {
@@ -296,7 +353,7 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
                 sink.put(dst, g0 + lane, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_OK));
             }
         } else {
-            D.sh_min = mem;
+            if (memo) D.sh_min = mem;
             sink.fail(dst, 1, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT);
         }
     }
@@ -308,8 +365,8 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
 template <class Get, class Sink>
 __device__ __noinline__ uint32_t node_step_cold(Lane& L, Dead& D, uint32_t lane, uint32_t g0,
                                                 const uint32_t* __restrict__ tbl_s, Get get, uint32_t k,
-                                                uint32_t cnt, Sink& sink, bool have_off) {
-    return node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, have_off);
+                                                uint32_t cnt, Sink& sink, bool have_off, const SelCtx sc) {
+    return node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, have_off, sc);
 }
 
 // ====================================================================================================
@@ -604,6 +661,7 @@ struct PackArgs {
     uint2* out;
     uint32_t n_out, n_node, have_off;
     Err err;
+    SelCtx sel;                   // optional GPU attributes + selector table (spec §10)
     PeerTail peer;                // world == 0: single GPU                            (k_fused)
     unsigned long long* timeline; // optional instrumentation: 8 clock stamps per CTA  (k_fused), else NULL
 };
@@ -671,6 +729,7 @@ struct NodeCtx {
     uint32_t tbl_addr;             // shared: placement table (u32 cells)
     const uint32_t* tbl_ptr;       // same table for the generic step
     bool homog, mig_ok, mig_offer, have_off;
+    SelCtx sc;
     bool prof_on = false;          // instrumentation: cycle accumulators of the three parts of segment_run
     long long t_pre = 0, t_loop = 0, t_epi = 0; uint32_t n_live = 0;
 
@@ -704,13 +763,15 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     const uint32_t dst = c.y, mem = c.z, group = c.w;
     bool live = present && pos >= x.k_next;
     const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : prof;
-    if (live && claim_invalid(kind, prof, count, x.have_off)) {            // spec §3
+    const uint32_t sel = claim_sel(kind, mem, group);
+    if (live && claim_invalid(kind, prof, count, x.have_off)) {            // spec §3 (unknown selector ids: generic step)
         if (dst < sink.n_out) sink.put(dst, DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
         else sink.err.set(ERR_OUT_RANGE);
         live = false;
     }
     const uint32_t slots = kind == DRA_KIND_GPU ? count : 1u;
-    const bool is_group = kind == DRA_KIND_MIG && group != 0;
+    // co-location runs and claims with a selector take the generic step (own range checks, no failure memo)
+    const bool is_group = (kind == DRA_KIND_MIG && group != 0) || sel != 0;
     if (live && !is_group && (dst > sink.n_out || slots > sink.n_out - dst)) { sink.err.set(ERR_OUT_RANGE); live = false; }
     if (live && !is_group) {                                               // shapes that already failed here
         bool dead = false; uint32_t st = DRA_ST_NO_CAPACITY;
@@ -804,14 +865,14 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             }
         } else {                                           // co-location run: generic step (emits its own records)
             const uint32_t pj = r0.x;
-            if (pj >= x.k_next) x.k_next = pj + node_step_cold(L, D, lane, g0, x.tbl_ptr, get, pj, cnt, sink, x.have_off);
+            if (pj >= x.k_next) x.k_next = pj + node_step_cold(L, D, lane, g0, x.tbl_ptr, get, pj, cnt, sink, x.have_off, x.sc);
         }
     };
     // Common case — every live record of the segment is a plain MIG claim on a homogeneous node: a loop with
     // no class dispatch and no divergent branch.  Winner = lowest set bit of the ballot (b & -b, no FLO on the
     // chain), placement bits = sizebits * lowest-candidate-bit (a multiply by a one-hot is the shift).
     const bool fast = x.homog && __ballot_sync(FULLMASK, live && (is_group || kind != DRA_KIND_MIG)) == 0;
-    const bool fast_sh = !fast && __ballot_sync(FULLMASK, live && kind != DRA_KIND_SHARED) == 0;
+    const bool fast_sh = !fast && __ballot_sync(FULLMASK, live && (is_group || kind != DRA_KIND_SHARED)) == 0;
     const uint32_t lanebit = 1u << lane;
     if (fast_sh) {
         // every live record is a SHARED claim (spec §7): flags cannot change inside the segment
@@ -942,6 +1003,7 @@ k_pack(const PackArgs a) {
     x.live_addr = wbase + PK_LIVE; x.tbl_addr = sbase + PK_TBL;
     x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + PK_TBL);
     x.have_off = a.have_off != 0;
+    x.sc = a.sel;
     x.sink = OutSink{a.out, a.n_out, a.err, lane};
 
     uint32_t segbase = 0;      // running segment counter: ring slot = (segbase+q) % RING
@@ -1170,6 +1232,7 @@ k_fused(const PackArgs a) {
             x.live_addr = sbase + FU_LIVE; x.tbl_addr = sbase + FU_TBL;
             x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + FU_TBL);
             x.have_off = a.have_off != 0;
+            x.sc = a.sel;
             x.sink = OutSink{a.out, a.n_out, a.err, lane};
             x.g0 = g0;
             mbar_wait_a(tbar, 0);
@@ -1249,6 +1312,7 @@ struct UnsArgs {
     uint32_t n_pair;
     const uint4* inv; const uint32_t* node_off; uint32_t n_node; const uint32_t* tbl;
     uint32_t* bits;     // n_pair bits, zeroed by the caller, set with atomicOr
+    SelCtx sel;
 };
 
 struct GlobalGet {
@@ -1277,7 +1341,7 @@ k_unsuitable(const UnsArgs a) {
         Lane L; L.load(rec, lane < ng);
         Dead D; FlagSink sink; GlobalGet get{a.claims + c0};
         uint32_t k = 0;
-        while (k < cnt && !sink.stop()) k += node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, true);
+        while (k < cnt && !sink.stop()) k += node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, true, a.sel);
         if (!sink.failed && lane == 0) atomicOr(&a.bits[pair >> 5], 1u << (pair & 31));
     }
 }

@@ -33,6 +33,34 @@ OUT_DTYPE = np.dtype([("gpu", "<u4"), ("start", "u1"), ("size", "u1"), ("profile
                       ("status", "u1")])
 PROF_DTYPE = np.dtype([("size", "u1"), ("rsvd", "u1"), ("start_mask", "<u2")])
 
+# selectors (spec §10)
+ATTR_DTYPE = np.dtype([("mem_total_mib", "<u4"), ("cc", "<u4"), ("index", "<u4"), ("product", "<u2"),
+                       ("driver_major", "<u2")])
+SEL_INS_DTYPE = np.dtype([("op", "u1"), ("attr", "u1"), ("cmp", "u1"), ("rsvd", "u1"), ("value", "<u4")])
+SEL_MAX_INS = 8
+SEL_END, SEL_CMP, SEL_AND, SEL_OR, SEL_NOT = 0, 1, 2, 3, 4
+ATTR_MEMORY_MIB, ATTR_CC, ATTR_INDEX, ATTR_PRODUCT, ATTR_DRIVER_MAJOR = 0, 1, 2, 3, 4
+CMP_EQ, CMP_NE, CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_IN_MASK = 0, 1, 2, 3, 4, 5, 6
+assert ATTR_DTYPE.itemsize == 16 and SEL_INS_DTYPE.itemsize == 8
+
+
+def selector(*ins) -> np.ndarray:
+    """Build one selector program from ('cmp', attr, cmp, value) / 'and' / 'or' / 'not' items (postfix)."""
+    prog = np.zeros(SEL_MAX_INS, dtype=SEL_INS_DTYPE)
+    assert len(ins) <= SEL_MAX_INS
+    for i, it in enumerate(ins):
+        if it == "and":
+            prog[i]["op"] = SEL_AND
+        elif it == "or":
+            prog[i]["op"] = SEL_OR
+        elif it == "not":
+            prog[i]["op"] = SEL_NOT
+        else:
+            _, attr, cmp_, val = it
+            prog[i] = (SEL_CMP, attr, cmp_, 0, val)
+    return prog
+
+
 assert GPU_DTYPE.itemsize == 16 and CLAIM_DTYPE.itemsize == 16
 assert OUT_DTYPE.itemsize == 8 and PROF_DTYPE.itemsize == 4
 

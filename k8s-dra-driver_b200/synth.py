@@ -214,4 +214,39 @@ def mixed(n_claim: int = 4000, n_node: int = 37, seed: int = 7, invalid: bool = 
     return w
 
 
+def with_selectors(w: Workload, seed: int = 1, frac: int = 3):
+    """Adds GPU attributes, a selector table (spec §10) and selector ids on ~1/frac of the claims of `w`.
+    Returns (attrs, sels).  Shapes follow demo/specs/selectors/parameters.yaml:7-27 (memory / compute
+    capability comparisons under and-expressions) and demo/specs/quickstart/gpu-test6.yaml:23-31
+    (product match && index in a set)."""
+    r = splitmix64(BASE_SEED + 900 + seed, 4 * max(w.n_gpu, 1) + 2 * w.n_claim + 8)
+    ng = w.n_gpu
+    a = np.zeros(ng, dtype=R.ATTR_DTYPE)
+    a["mem_total_mib"] = np.array([16384, 40960, 81920], dtype=np.uint32)[(r[0:ng] % np.uint64(3)).astype(np.int64)]
+    a["cc"] = np.array([0x0705, 0x0800, 0x0900], dtype=np.uint32)[(r[ng:2 * ng] % np.uint64(3)).astype(np.int64)]
+    a["index"] = np.arange(ng, dtype=np.uint32) - np.repeat(w.node_off[:-1], np.diff(w.node_off)).astype(np.uint32)
+    a["product"] = (r[2 * ng:3 * ng] % np.uint64(4)).astype(np.uint16)
+    a["driver_major"] = np.array([535, 550, 570], dtype=np.uint16)[(r[3 * ng:4 * ng] % np.uint64(3)).astype(np.int64)]
+    S_ = R.selector
+    sels = np.stack([
+        S_(("cmp", R.ATTR_MEMORY_MIB, R.CMP_LE, 16384), ("cmp", R.ATTR_CC, R.CMP_GE, 0x0705), "and"),   # "inference-gpu"
+        S_(("cmp", R.ATTR_MEMORY_MIB, R.CMP_GE, 40960)),                                                  # "training-gpu"
+        S_(("cmp", R.ATTR_PRODUCT, R.CMP_IN_MASK, 0b0110), ("cmp", R.ATTR_INDEX, R.CMP_IN_MASK, 0b01010101), "and"),
+        S_(("cmp", R.ATTR_CC, R.CMP_LT, 0x0800), "not"),
+        S_("and"),                                                                                         # malformed: false
+        S_(),                                                                                              # empty: true
+        S_(("cmp", R.ATTR_DRIVER_MAJOR, R.CMP_NE, 535), ("cmp", R.ATTR_INDEX, R.CMP_GT, 1), "or",
+           ("cmp", R.ATTR_MEMORY_MIB, R.CMP_EQ, 81920), "or"),
+    ])
+    pick = r[4 * ng: 4 * ng + w.n_claim]
+    sid = (r[4 * ng + w.n_claim: 4 * ng + 2 * w.n_claim] % np.uint64(len(sels) + 2)).astype(np.uint32) + 1   # a few beyond the table
+    use = (pick % np.uint64(frac)) == 0
+    c = w.claims
+    gm = use & ((c["kind"] == R.KIND_GPU) | (c["kind"] == R.KIND_MIG))
+    c["mem_limit_mib"] = np.where(gm, sid, c["mem_limit_mib"])
+    sh = use & (c["kind"] == R.KIND_SHARED)
+    c["group"] = np.where(sh, sid, c["group"])
+    return a, sels
+
+
 CONFIGS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}

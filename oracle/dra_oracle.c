@@ -27,8 +27,72 @@ static uint8_t out_profile(const dra_claim_rec* c)
     return c->profile;
 }
 
-/* spec §3 */
-static int claim_invalid(const dra_claim_rec* c, uint32_t n_node, int have_off)
+/* ---- selectors, spec §10 ------------------------------------------------------------------------- */
+static const dra_gpu_attr* g_attrs; static uint32_t g_nattr;
+static const dra_selector* g_sels; static uint32_t g_nsel;
+
+void dra_oracle_set_selectors(const dra_gpu_attr* attrs, uint32_t n_gpu, const dra_selector* sels, uint32_t n_sel)
+{
+    g_attrs = attrs; g_nattr = n_gpu; g_sels = sels; g_nsel = n_sel;
+}
+
+static uint32_t claim_sel(const dra_claim_rec* c)
+{
+    if (c->kind == DRA_KIND_GPU || c->kind == DRA_KIND_MIG) return c->mem_limit_mib;
+    if (c->kind == DRA_KIND_SHARED) return c->group;
+    return 0;
+}
+
+/* does global GPU `g` pass selector `id` (0 = no selector)?  Postfix program over a boolean stack. */
+static int sel_pass(uint32_t id, uint32_t g)
+{
+    if (id == 0) return 1;
+    if (id > g_nsel) return 0;
+    dra_gpu_attr a; memset(&a, 0, sizeof a);
+    if (g_attrs && g < g_nattr) a = g_attrs[g];
+    const dra_selector* s = &g_sels[id - 1];
+    int stack[DRA_SEL_MAX_INS + 1]; int sp = 0; int any = 0;
+    for (uint32_t i = 0; i < DRA_SEL_MAX_INS; i++) {
+        const dra_sel_ins* in = &s->ins[i];
+        if (in->op == DRA_SEL_END) break;
+        any = 1;
+        if (in->op == DRA_SEL_CMP) {
+            uint32_t v;
+            switch (in->attr) {
+                case DRA_ATTR_MEMORY_MIB: v = a.mem_total_mib; break;
+                case DRA_ATTR_CC: v = a.cc; break;
+                case DRA_ATTR_INDEX: v = a.index; break;
+                case DRA_ATTR_PRODUCT: v = a.product; break;
+                case DRA_ATTR_DRIVER_MAJOR: v = a.driver_major; break;
+                default: return 0;
+            }
+            int r;
+            switch (in->cmp) {
+                case DRA_CMP_EQ: r = v == in->value; break;
+                case DRA_CMP_NE: r = v != in->value; break;
+                case DRA_CMP_LT: r = v < in->value; break;
+                case DRA_CMP_LE: r = v <= in->value; break;
+                case DRA_CMP_GT: r = v > in->value; break;
+                case DRA_CMP_GE: r = v >= in->value; break;
+                case DRA_CMP_IN_MASK: r = v < 32 && ((in->value >> v) & 1u); break;
+                default: return 0;
+            }
+            stack[sp++] = r;
+        } else if (in->op == DRA_SEL_AND || in->op == DRA_SEL_OR) {
+            if (sp < 2) return 0;
+            int b = stack[--sp], a_ = stack[--sp];
+            stack[sp++] = in->op == DRA_SEL_AND ? (a_ && b) : (a_ || b);
+        } else if (in->op == DRA_SEL_NOT) {
+            if (sp < 1) return 0;
+            stack[sp - 1] = !stack[sp - 1];
+        } else return 0;
+    }
+    if (!any) return 1;
+    return sp >= 1 ? stack[sp - 1] : 0;
+}
+
+/* spec §3: malformed shape (decides the number of slots) */
+static int claim_bad_shape(const dra_claim_rec* c, uint32_t n_node, int have_off)
 {
     if (c->kind > DRA_KIND_SHARED) return 1;
     if (c->node >= n_node) return 1;
@@ -40,10 +104,16 @@ static int claim_invalid(const dra_claim_rec* c, uint32_t n_node, int have_off)
     return 0;
 }
 
+/* spec §3 + §10: INVALID = malformed shape, or a selector id beyond the table (keeps its slots) */
+static int claim_invalid(const dra_claim_rec* c, uint32_t n_node, int have_off)
+{
+    return claim_bad_shape(c, n_node, have_off) || claim_sel(c) > g_nsel;
+}
+
 /* spec §1: slots(c) */
 static uint32_t claim_slots(const dra_claim_rec* c, uint32_t n_node, int have_off)
 {
-    if (claim_invalid(c, n_node, have_off)) return 1;
+    if (claim_bad_shape(c, n_node, have_off)) return 1;
     return c->kind == DRA_KIND_GPU ? c->count : 1;
 }
 
@@ -99,17 +169,18 @@ static void do_gpu(node_job* j, uint32_t ci)
     const dra_claim_rec* c = &j->claims[ci];
     dra_out_rec* o = slot_of(j, ci);
     uint32_t elig = 0;
+    const uint32_t sel = claim_sel(c);
     for (uint32_t g = 0; g < j->ng; g++) {
         const dra_gpu_rec* r = &j->gpus[g];
         if (!(r->flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE)) &&
-            r->share_cnt == 0) elig++;
+            r->share_cnt == 0 && sel_pass(sel, j->g0 + g)) elig++;
     }
     if (elig < c->count) { fail_all(o, c->count, c, DRA_ST_NO_CAPACITY); j->all_ok = 0; return; }
     uint32_t k = 0;
     for (uint32_t g = 0; g < j->ng && k < c->count; g++) {
         dra_gpu_rec* r = &j->gpus[g];
         if (!(r->flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE)) &&
-            r->share_cnt == 0) {
+            r->share_cnt == 0 && sel_pass(sel, j->g0 + g)) {
             r->flags |= DRA_GPU_FULL_ALLOCATED;
             put(&o[k++], j->g0 + g, 0, 0, DRA_PROFILE_GPU, DRA_ST_OK);
         }
@@ -125,7 +196,7 @@ static void do_mig(node_job* j, uint32_t ci)
     for (uint32_t g = 0; g < j->ng; g++) {
         dra_gpu_rec* r = &j->gpus[g];
         dra_prof_ent e = j->tbl[r->model].ent[c->profile];
-        if (!gpu_offers(r, e)) continue;
+        if (!gpu_offers(r, e) || !sel_pass(claim_sel(c), j->g0 + g)) continue;
         any_offer = 1;
         if (r->flags & DRA_GPU_FULL_ALLOCATED) continue;
         int s = lowest_fit(r->busy, e);
@@ -145,6 +216,7 @@ static void do_group(node_job* j, uint32_t i0, uint32_t i1)
         dra_gpu_rec* r = &j->gpus[g];
         if (!(r->flags & DRA_GPU_MIG_ENABLED)) continue;
         if (r->flags & (DRA_GPU_UNAVAILABLE | DRA_GPU_FULL_ALLOCATED)) continue;
+        if (!sel_pass(claim_sel(&j->claims[j->idx[i0]]), j->g0 + g)) continue;   /* first member's selector */
         uint16_t busy = r->busy;
         int starts[DRA_MAX_GROUP];
         int ok = 1;
@@ -182,6 +254,7 @@ static void do_shared(node_job* j, uint32_t ci)
         if (r->flags & (DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE)) continue;
         if (r->share_cnt == 0xFFFFu) continue;
         if (r->mem_free_mib < c->mem_limit_mib) continue;
+        if (!sel_pass(claim_sel(c), j->g0 + g)) continue;
         r->mem_free_mib -= c->mem_limit_mib;
         r->share_cnt++;
         put(o, j->g0 + g, 0, 0, DRA_PROFILE_SHARED, DRA_ST_OK);
@@ -210,7 +283,7 @@ static void node_process(node_job* j)
         dra_claim_rec c = j->claims[ci];
         if (j->use_override) c.node = j->node_override;
         if (claim_invalid(&c, j->n_node, have_off)) {
-            put(slot_of(j, ci), DRA_GPU_NONE, 0, 0, out_profile(&c), DRA_ST_INVALID);
+            fail_all(slot_of(j, ci), claim_slots(&c, j->n_node, have_off), &c, DRA_ST_INVALID);
             j->all_ok = 0; i++; continue;
         }
         if (c.kind == DRA_KIND_MIG && c.group != 0) {

@@ -31,6 +31,10 @@ int dra_oracle_allocate_mt(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* no
                            const dra_claim_rec* claims, uint32_t n_claim,
                            const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, int n_threads);
 
+/* Optional selector context for the calls that follow (spec §10); pass NULL / 0 to clear.  Not thread-safe
+ * with respect to concurrent calls (test infrastructure). */
+void dra_oracle_set_selectors(const dra_gpu_attr* attrs, uint32_t n_gpu, const dra_selector* sels, uint32_t n_sel);
+
 /* UnsuitableNodes (spec §8).  gpus is read-only. */
 int dra_oracle_unsuitable(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off,
                           uint32_t n_node, const dra_profile_tbl* tbl,

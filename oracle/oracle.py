@@ -50,6 +50,8 @@ def lib():
         _lib.dra_oracle_unsuitable.restype = i32
         _lib.dra_oracle_deallocate.argtypes = [vp, u32, vp, u32, vp, vp, u32]
         _lib.dra_oracle_deallocate.restype = i32
+        _lib.dra_oracle_set_selectors.argtypes = [vp, u32, vp, u32]
+        _lib.dra_oracle_set_selectors.restype = None
         _lib.dra_oracle_megabyte.argtypes = [C.c_int64, C.POINTER(C.c_int)]
         _lib.dra_oracle_megabyte.restype = C.c_int64
         _lib.dra_oracle_imex_offset.argtypes = [vp, u32, C.c_int32, C.c_int32]
@@ -109,6 +111,21 @@ def deallocate(gpus, claims, out, out_off=None):
     if rc != 0:
         raise ValueError(f"dra_oracle_deallocate: rc={rc}")
     return g
+
+
+_sel_keep = []
+
+
+def set_selectors(attrs=None, sels=None):
+    """Selector context for the following calls (spec §10); call with no arguments to clear."""
+    _sel_keep.clear()
+    if sels is None or len(sels) == 0:
+        lib().dra_oracle_set_selectors(None, 0, None, 0)
+        return
+    a = np.ascontiguousarray(attrs) if attrs is not None else np.zeros(0, dtype=np.uint8)
+    s_ = np.ascontiguousarray(sels).reshape(-1, 8)
+    _sel_keep.extend([a, s_])                  # the C side keeps the pointers
+    lib().dra_oracle_set_selectors(_p(a) if len(a) else None, len(a), _p(s_), len(s_))
 
 
 def megabyte(nbytes: int):

@@ -213,3 +213,32 @@ def test_launch_counter_counts_our_kernels(pkg, ctx):
     before = ctx.launch_count()
     ctx.allocate(w.claims)
     assert ctx.launch_count() - before == 4          # hist, scan, scatter, pack
+
+
+# ---- selectors on the device (spec §10) -----------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(4))
+def test_selectors_match_oracle(pkg, ctx, oracle, seed):
+    w = pkg.synth.mixed([300, 2500, 6000, 12000][seed], [5, 40, 90, 160][seed], 200 + seed, invalid=seed % 2 == 0)
+    attrs, sels = pkg.synth.with_selectors(w, seed)
+    ctx.set_table(w.table); ctx.set_inventory(w.gpus, w.node_off)
+    ctx.set_gpu_attrs(attrs); ctx.set_selectors(sels)
+    oracle.set_selectors(attrs, sels)
+    try:
+        out = ctx.allocate(w.claims, w.out_off, w.n_out)
+        inv = ctx.get_inventory()
+        ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+        _assert_same(out, inv, ref_out, ref_inv, f"selectors seed {seed}")
+        # UnsuitableNodes sees the same selectors
+        pod_off = np.arange(0, len(w.claims) + 1, 3, dtype=np.uint32)
+        if pod_off[-1] != len(w.claims):
+            pod_off = np.append(pod_off, len(w.claims)).astype(np.uint32)
+        n_pod = len(pod_off) - 1
+        cand_off = (np.arange(n_pod + 1, dtype=np.uint32) * 2)
+        cand_nodes = (np.arange(2 * n_pod, dtype=np.uint32) * 13) % np.uint32(w.n_node)
+        ctx.set_inventory(w.gpus, w.node_off)
+        got = ctx.unsuitable(w.claims, pod_off, cand_nodes, cand_off)
+        ref = oracle.unsuitable(w.gpus, w.node_off, w.table, w.claims, pod_off, cand_nodes, cand_off)
+        assert got.tobytes() == ref.tobytes()
+    finally:
+        oracle.set_selectors()
+        ctx.set_selectors(None); ctx.set_gpu_attrs(None)

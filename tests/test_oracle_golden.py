@@ -174,3 +174,45 @@ def test_imex_offset_search(oracle):
     assert oracle.imex_offset([]) == 0
     assert oracle.imex_offset([0, 128, 384]) == 256
     assert oracle.imex_offset(list(range(0, 2048, 128))) == -1
+
+
+# ---- selectors (spec §10): the legacy GpuClaimParameters.selector shapes, demo/specs/selectors/parameters.yaml:7-27
+def test_selectors_inference_and_training_shapes(pkg, oracle):
+    R = pkg.records
+    g, off = R.make_inventory([4], mig=False)
+    attrs = np.zeros(4, dtype=R.ATTR_DTYPE)
+    attrs["mem_total_mib"] = [81920, 15258, 40960, 15258]          # "16G" = 15258 MiB by limit.Megabyte arithmetic
+    attrs["cc"] = [0x0900, 0x0700, 0x0800, 0x0705]
+    attrs["index"] = np.arange(4)
+    mem16g = pkg.sharing.megabyte_mib("16G")
+    sels = np.stack([
+        R.selector(("cmp", R.ATTR_MEMORY_MIB, R.CMP_LE, mem16g), ("cmp", R.ATTR_CC, R.CMP_GE, 0x0705), "and"),  # inference-gpu
+        R.selector(("cmp", R.ATTR_MEMORY_MIB, R.CMP_GE, mem16g)),                                                # training-gpu
+    ])
+    c = np.zeros(4, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_GPU; c["count"] = 1
+    c["mem_limit_mib"] = [1, 2, 1, 9]                    # inference, training, inference again, unknown selector
+    oracle.set_selectors(attrs, sels)
+    try:
+        out, _ = oracle.allocate(g, off, R.default_table(), c)
+    finally:
+        oracle.set_selectors()
+    # inference: <=16G and cc>=7.5 -> only gpu 3; training: >=16G -> lowest is gpu 0; second inference: none left
+    assert list(out["gpu"]) == [3, 0, 0xFFFFFFFF, 0xFFFFFFFF]
+    assert list(out["status"]) == [0, 0, 1, 5]
+
+
+def test_selector_programs_edge_cases(pkg, oracle):
+    R = pkg.records
+    w = pkg.synth.mixed(400, 6, 2, invalid=False)
+    attrs, sels = pkg.synth.with_selectors(w, 3)
+    oracle.set_selectors(attrs, sels)
+    try:
+        out, inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+    finally:
+        oracle.set_selectors()
+    sid = np.where(w.claims["kind"] == R.KIND_SHARED, w.claims["group"], w.claims["mem_limit_mib"])
+    first = out[w.out_off]
+    assert np.all(first["status"][sid > len(sels)] == 5)                  # ids beyond the table: INVALID
+    assert not np.any(first["status"][sid == 5] == 0)                      # the malformed program passes nothing
+    assert np.any(first["status"][(sid > 0) & (sid <= len(sels))] == 0)    # and real selectors do allocate
