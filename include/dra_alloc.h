@@ -223,7 +223,9 @@ int  dra_ctx_sync(dra_ctx* ctx);
  * batched over pods.  Pure: evaluates each pod's claims on a snapshot of each candidate node.
  *   pod_off[n_pod+1]   claim range of each pod
  *   cand_off[n_pod+1]  range of each pod's candidates in cand_nodes
- *   suitable_bits      ceil(cand_off[n_pod]/8) bytes; bit k = k-th (pod,candidate) pair is suitable */
+ *   suitable_bits      ceil(cand_off[n_pod]/8) bytes; bit k = k-th (pod,candidate) pair is suitable
+ * Dense form: cand_nodes == NULL and cand_off == NULL evaluates every pod against EVERY node of the inventory
+ * (pair k = pod * n_node + node; suitable_bits has ceil(n_pod*n_node/8) bytes) without any candidate arrays. */
 int  dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim,
                           const uint32_t* pod_off, uint32_t n_pod,
                           const uint32_t* cand_nodes, const uint32_t* cand_off,

@@ -227,9 +227,15 @@ class Context:
                                                                _ptr(d_out_off), _ptr(d_out_all), n_out,
                                                                n_per_rank, flags))
 
-    def unsuitable(self, claims, pod_off, cand_nodes, cand_off) -> np.ndarray:
+    def unsuitable(self, claims, pod_off, cand_nodes=None, cand_off=None) -> np.ndarray:
+        """cand_nodes/cand_off None = dense form: every pod against every node (bit k = pod * n_node + node)."""
         c = np.ascontiguousarray(claims, dtype=R.CLAIM_DTYPE)
         po = np.ascontiguousarray(pod_off, dtype=np.uint32)
+        if cand_nodes is None:
+            n_pair = (len(po) - 1) * self.n_node
+            bits = np.zeros((n_pair + 7) // 8 + 8, dtype=np.uint8)
+            self._check(self._lib.dra_unsuitable_batch(self._h, _ptr(c), len(c), _ptr(po), len(po) - 1, None, None, _ptr(bits)))
+            return bits[: (n_pair + 7) // 8]
         cn = np.ascontiguousarray(cand_nodes, dtype=np.uint32)
         co = np.ascontiguousarray(cand_off, dtype=np.uint32)
         n_pair = int(co[-1])

@@ -70,7 +70,7 @@ struct dra_ctx {
     uint32_t cfg_flags = 0;
 
     // inventory
-    uint32_t n_gpu = 0, n_node = 0;
+    uint32_t n_gpu = 0, n_node = 0, max_width = 0;     // max_width: most GPUs on one node
     uint4* d_inv_live = nullptr;
     uint4* d_inv_pristine = nullptr;
     uint32_t* d_node_off = nullptr;
@@ -81,7 +81,7 @@ struct dra_ctx {
     uint4* d_sels = nullptr;   uint32_t n_sel = 0;
 
     // batch buffers (device)
-    size_t cap_claims = 0, cap_out = 0, cap_hist = 0, cap_nodes = 0, cap_pairs = 0, cap_pods = 0;
+    size_t cap_claims = 0, cap_out = 0, cap_hist = 0, cap_nodes = 0, cap_pairs = 0, cap_pods = 0, cap_bits_only = 0;
     uint4* d_claims = nullptr;
     uint4* d_sorted = nullptr;
     uint32_t* d_out_off = nullptr;
@@ -466,6 +466,8 @@ int dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu, con
     if (n_gpu) CU(cudaMemcpy(ctx->d_inv_live, gpus, (size_t)n_gpu * 16, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_node_off, node_off, ((size_t)n_node + 1) * 4, cudaMemcpyHostToDevice));
     ctx->n_gpu = n_gpu; ctx->n_node = n_node;
+    ctx->max_width = 0;
+    for (uint32_t n = 0; n < n_node; ++n) ctx->max_width = std::max(ctx->max_width, node_off[n + 1] - node_off[n]);
     ctx->cap_hist = 0;  // histogram geometry depends on n_node
     if (ctx->d_hist) { CU(cudaFree(ctx->d_hist)); ctx->d_hist = nullptr; }
     return DRA_OK;
@@ -566,11 +568,15 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
 
 int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* pod_off, uint32_t n_pod,
                          const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits) {
-    if (!ctx || !pod_off || !cand_off || (n_claim && !claims)) return DRA_E_INVAL;
+    if (!ctx || !pod_off || (n_claim && !claims)) return DRA_E_INVAL;
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
     if (pod_off[n_pod] != n_claim) return fail(ctx, DRA_E_INVAL, "pod_off[n_pod] != n_claim");
-    const uint32_t n_pair = cand_off[n_pod];
-    if (n_pair && (!cand_nodes || !suitable_bits)) return DRA_E_INVAL;
+    const bool dense = cand_nodes == nullptr && cand_off == nullptr;      // every pod against every node
+    if (!dense && !cand_off) return DRA_E_INVAL;
+    const uint64_t n_pair64 = dense ? (uint64_t)n_pod * ctx->n_node : cand_off[n_pod];
+    if (n_pair64 > 0xFFFFFFF0ull) return fail(ctx, DRA_E_INVAL, "too many (pod, node) pairs");
+    const uint32_t n_pair = (uint32_t)n_pair64;
+    if (n_pair && (!suitable_bits || (!dense && !cand_nodes))) return DRA_E_INVAL;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_batch(ctx, n_claim, 1, true);
     if (rc) return rc;
@@ -581,44 +587,60 @@ int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
         if ((rc = grow_nc(ctx, ctx->d_cand_off, 0, cap))) return rc;
         ctx->cap_pods = cap;
     }
-    if (n_pair + 64 > ctx->cap_pairs) {
+    const size_t words = ((size_t)n_pair + 31) / 32;
+    if (!dense && (size_t)n_pair + 64 > ctx->cap_pairs) {
         size_t cap = (size_t)n_pair + n_pair / 2 + 128;
         if ((rc = grow_nc(ctx, ctx->d_cand_nodes, 0, cap))) return rc;
         if ((rc = grow_nc(ctx, ctx->d_pair_pod, 0, cap))) return rc;
-        if ((rc = grow_nc(ctx, ctx->d_bits, 0, cap / 32 + 8))) return rc;
         ctx->cap_pairs = cap;
     }
-    const size_t words = ((size_t)n_pair + 31) / 32;
-    // pair -> pod expansion on the host side of the staging buffer (O(n_pair) integer fill)
-    const size_t stage = (size_t)n_claim * 16 + ((size_t)n_pod + 1) * 8 + (size_t)n_pair * 8 + words * 4 + 64;
+    if (words + 8 > ctx->cap_bits_only) {
+        size_t cap = words + words / 2 + 64;
+        if ((rc = grow_nc(ctx, ctx->d_bits, 0, cap))) return rc;
+        ctx->cap_bits_only = cap;
+    }
+    // staging: claims | pod_off | (cand_off | cand_nodes | pair->pod expansion)
+    const size_t stage = (size_t)n_claim * 16 + ((size_t)n_pod + 1) * 8 + (dense ? 0 : (size_t)n_pair * 8) + 64;
     if ((rc = grow_pinned(ctx, ctx->h_in, ctx->h_in_cap, stage))) return rc;
     uint8_t* p = ctx->h_in;
-    memcpy(p, claims, (size_t)n_claim * 16); uint8_t* h_claims = p; p += (size_t)n_claim * 16;
+    if (n_claim) memcpy(p, claims, (size_t)n_claim * 16);
+    uint8_t* h_claims = p; p += (size_t)n_claim * 16;
     memcpy(p, pod_off, ((size_t)n_pod + 1) * 4); uint8_t* h_pod = p; p += ((size_t)n_pod + 1) * 4;
-    memcpy(p, cand_off, ((size_t)n_pod + 1) * 4); uint8_t* h_coff = p; p += ((size_t)n_pod + 1) * 4;
-    if (n_pair) memcpy(p, cand_nodes, (size_t)n_pair * 4);
-    uint8_t* h_cn = p; p += (size_t)n_pair * 4;
-    uint32_t* h_pp = (uint32_t*)p;
-    for (uint32_t q = 0; q < n_pod; ++q) {
-        if (cand_off[q + 1] < cand_off[q] || cand_off[q + 1] > n_pair) return fail(ctx, DRA_E_INVAL, "cand_off not monotone at pod %u", q);
+    for (uint32_t q = 0; q < n_pod; ++q)
         if (pod_off[q + 1] < pod_off[q]) return fail(ctx, DRA_E_INVAL, "pod_off not monotone at pod %u", q);
-        for (uint32_t k = cand_off[q]; k < cand_off[q + 1]; ++k) h_pp[k] = q;
+    uint8_t *h_cn = nullptr; uint32_t* h_pp = nullptr;
+    if (!dense) {
+        p += ((size_t)n_pod + 1) * 4;                    // (cand_off is only needed on the host)
+        if (n_pair) memcpy(p, cand_nodes, (size_t)n_pair * 4);
+        h_cn = p; p += (size_t)n_pair * 4;
+        h_pp = (uint32_t*)p;
+        for (uint32_t q = 0; q < n_pod; ++q) {
+            if (cand_off[q + 1] < cand_off[q] || cand_off[q + 1] > n_pair) return fail(ctx, DRA_E_INVAL, "cand_off not monotone at pod %u", q);
+            for (uint32_t k = cand_off[q]; k < cand_off[q + 1]; ++k) h_pp[k] = q;
+        }
     }
     if (n_claim) CU(cudaMemcpyAsync(ctx->d_claims, h_claims, (size_t)n_claim * 16, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_pod_off, h_pod, ((size_t)n_pod + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_cand_off, h_coff, ((size_t)n_pod + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (n_pair) {
-        CU(cudaMemcpyAsync(ctx->d_cand_nodes, h_cn, (size_t)n_pair * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_pair_pod, h_pp, (size_t)n_pair * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!dense) {
+            CU(cudaMemcpyAsync(ctx->d_cand_nodes, h_cn, (size_t)n_pair * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->d_pair_pod, h_pp, (size_t)n_pair * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
         CU(cudaMemsetAsync(ctx->d_bits, 0, words * 4, ctx->stream));
-        UnsArgs a;
+        UnsArgs a; memset(&a, 0, sizeof a);
         a.claims = ctx->d_claims; a.pod_off = ctx->d_pod_off; a.n_pod = n_pod;
         a.cand_nodes = ctx->d_cand_nodes; a.cand_off = ctx->d_cand_off; a.pair_pod = ctx->d_pair_pod; a.n_pair = n_pair;
         a.inv = ctx->d_inv_live; a.node_off = ctx->d_node_off; a.n_node = ctx->n_node; a.tbl = ctx->d_tbl; a.bits = ctx->d_bits;
         a.sel = sel_of(ctx);
+        a.dense = dense ? 1u : 0u;
         Prof prof(ctx);
-        uint32_t grid = std::min((n_pair + 7) / 8, 148u * 8u);
-        k_unsuitable<8><<<grid, 256, 0, ctx->stream>>>(a);
+        // lanes per pair from the widest node: 8 lanes = 4 pairs per warp
+        const uint32_t W = ctx->max_width <= 8 ? 8u : (ctx->max_width <= 16 ? 16u : 32u);
+        const uint32_t per_cta = 8 * (32 / W);
+        const uint32_t grid = std::max(1u, std::min((n_pair + per_cta - 1) / per_cta, 148u * 8u));
+        if (W == 8) k_unsuitable<8, 8><<<grid, 256, 0, ctx->stream>>>(a);
+        else if (W == 16) k_unsuitable<8, 16><<<grid, 256, 0, ctx->stream>>>(a);
+        else k_unsuitable<8, 32><<<grid, 256, 0, ctx->stream>>>(a);
         prof.mark();
         ctx->launches += 1;
         if ((rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, words * 4))) return rc;

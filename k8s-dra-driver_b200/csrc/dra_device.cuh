@@ -228,7 +228,11 @@ __device__ __forceinline__ bool claim_invalid(uint32_t kind, uint32_t prof, uint
 template <class Get, class Sink>
 __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, uint32_t g0,
                                               const uint32_t* __restrict__ tbl_s, Get get, uint32_t k,
-                                              uint32_t cnt, Sink& sink, bool have_off, const SelCtx sc) {
+                                              uint32_t cnt, Sink& sink, bool have_off, const SelCtx sc,
+                                              const uint32_t gmask = FULLMASK, const uint32_t gbase = 0) {
+    // `lane` is the absolute lane; the node's GPUs sit on lanes gbase .. of the sub-warp group `gmask`
+    // (the whole warp for the pack kernels; 8/16-lane groups in k_unsuitable).  Ballots are restricted to
+    // the group, so __ffs(b)-1 is still the absolute lane of the lowest GPU.
     const uint4 c = get(k);
     const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
     const uint32_t dst = c.y, group = c.w;
@@ -237,7 +241,7 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
     const uint32_t mem = kind == DRA_KIND_SHARED ? c.z : 0u;
     // a claim with a selector sees its own subset of GPUs: the node-wide failure memo does not apply to it
     const bool memo = sel == 0;
-    const bool selok = sel == 0 ? true : sel_pass(sc, sel, g0 + lane, L.valid);
+    const bool selok = sel == 0 ? true : sel_pass(sc, sel, g0 + lane - gbase, L.valid);
 
     if (claim_invalid(kind, prof, count, have_off) || sel > sc.n_sel) {   // spec §3, §10
         const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU
@@ -260,15 +264,15 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
                             && smask != 0 && selok;
         const bool elig = offers && !(L.flags & DRA_GPU_FULL_ALLOCATED);
         const uint32_t cand = elig ? (fit_map(~L.busy & 0xFFFFu, size) & smask) : 0u;
-        const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
+        const uint32_t b = (__ballot_sync(gmask, cand != 0) & gmask);
         if (b) {
             if (lane == (uint32_t)__ffs(b) - 1u) {                  // lowest GPU
                 const uint32_t st = (uint32_t)__ffs(cand) - 1u;     // lowest start
                 L.busy |= ((1u << size) - 1u) << st;
-                sink.put(dst, g0 + lane, meta(st, size, prof, DRA_ST_OK));
+                sink.put(dst, g0 + lane - gbase, meta(st, size, prof, DRA_ST_OK));
             }
         } else {
-            const bool any = __ballot_sync(FULLMASK, offers) != 0;
+            const bool any = (__ballot_sync(gmask, offers) & gmask) != 0;
             if (memo) { if (any) D.nocap |= pbit; else D.bad |= pbit; }
             sink.fail(dst, 1, prof, any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE);
         }
@@ -295,7 +299,7 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
             ok = ok && cd != 0;
             if (cd) tb |= ((1u << sz) - 1u) << ((uint32_t)__ffs(cd) - 1u);
         }
-        const uint32_t b = __ballot_sync(FULLMASK, ok);
+        const uint32_t b = (__ballot_sync(gmask, ok) & gmask);
         if (b) {
             if (lane == (uint32_t)__ffs(b) - 1u) {                  // winner replays and emits
                 uint32_t nb = L.busy;
@@ -306,7 +310,7 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
                     const uint32_t sm = en >> 16, sz = en & 0xFFu;
                     const uint32_t st = (uint32_t)__ffs(fit_map(~nb & 0xFFFFu, sz) & sm) - 1u;
                     nb |= ((1u << sz) - 1u) << st;
-                    if (sink.in_range(cm.y)) sink.put(cm.y, g0 + lane, meta(st, sz, pm, DRA_ST_OK));
+                    if (sink.in_range(cm.y)) sink.put(cm.y, g0 + lane - gbase, meta(st, sz, pm, DRA_ST_OK));
                 }
                 L.busy = nb;
             }
@@ -327,12 +331,12 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
         if (!sink.range(dst, count)) return 1;
         if (memo && count >= D.gpu_min) { sink.fail(dst, count, DRA_PROFILE_GPU, DRA_ST_NO_CAPACITY); return 1; }
         const bool elig = L.valid && !(L.flags & BLOCKED) && L.share == 0 && selok;
-        const uint32_t b = __ballot_sync(FULLMASK, elig);
+        const uint32_t b = (__ballot_sync(gmask, elig) & gmask);
         if ((uint32_t)__popc(b) >= count) {
             const uint32_t r = (uint32_t)__popc(b & lanemask_lt());
             if (elig && r < count) {
                 L.flags |= DRA_GPU_FULL_ALLOCATED;
-                sink.put(dst + r, g0 + lane, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_OK));
+                sink.put(dst + r, g0 + lane - gbase, meta(0, 0, DRA_PROFILE_GPU, DRA_ST_OK));
             }
         } else {
             if (memo) D.gpu_min = count;
@@ -346,11 +350,11 @@ __device__ __forceinline__ uint32_t node_step(Lane& L, Dead& D, uint32_t lane, u
     if (memo && (uint64_t)mem >= D.sh_min) { sink.fail(dst, 1, DRA_PROFILE_SHARED, DRA_ST_MEM_LIMIT); return 1; }
     {
         const bool elig = L.valid && !(L.flags & BLOCKED) && L.share < 0xFFFFu && L.mem >= mem && selok;
-        const uint32_t b = __ballot_sync(FULLMASK, elig);
+        const uint32_t b = (__ballot_sync(gmask, elig) & gmask);
         if (b) {
             if (lane == (uint32_t)__ffs(b) - 1u) {
                 L.mem -= mem; L.share += 1;
-                sink.put(dst, g0 + lane, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_OK));
+                sink.put(dst, g0 + lane - gbase, meta(0, 0, DRA_PROFILE_SHARED, DRA_ST_OK));
             }
         } else {
             if (memo) D.sh_min = mem;
@@ -1313,6 +1317,7 @@ struct UnsArgs {
     const uint4* inv; const uint32_t* node_off; uint32_t n_node; const uint32_t* tbl;
     uint32_t* bits;     // n_pair bits, zeroed by the caller, set with atomicOr
     SelCtx sel;
+    uint32_t dense;     // 1: every pod x every node, pair = pod * n_node + node (cand arrays unused)
 };
 
 struct GlobalGet {
@@ -1320,29 +1325,39 @@ struct GlobalGet {
     __device__ __forceinline__ uint4 operator()(uint32_t m) const { return __ldg(&base[m]); }
 };
 
-template <int WPC>
+// W lanes per (pod, candidate) pair: 32/W pairs share a warp (W = 8 for the usual <= 8 GPUs per node), each
+// group running its own claim loop with group-wide ballots.  dense = every pod against every node
+// (pair = pod * n_node + node): no candidate arrays at all.
+template <int WPC, int W>
 __global__ void __launch_bounds__(WPC * 32, 2)
 k_unsuitable(const UnsArgs a) {
     __shared__ uint32_t tbl_s[DRA_MAX_MODELS * DRA_MAX_PROFILES];
     for (uint32_t i = threadIdx.x; i < DRA_MAX_MODELS * DRA_MAX_PROFILES; i += WPC * 32) tbl_s[i] = __ldg(&a.tbl[i]);
     __syncthreads();
+    constexpr uint32_t G = 32 / W;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t nwarps = gridDim.x * WPC;
-    for (uint32_t pair = blockIdx.x * WPC + wid; pair < a.n_pair; pair += nwarps) {
-        const uint32_t pod = __ldg(&a.pair_pod[pair]);
-        const uint32_t node = __ldg(&a.cand_nodes[pair]);
-        if (node >= a.n_node) continue;                               // unknown node: unsuitable
+    const uint32_t grp = lane / W, gl = lane % W, gbase = grp * W;
+    const uint32_t gmask = W == 32 ? FULLMASK : (((1u << (W & 31)) - 1u) << gbase);
+    const uint32_t stride = gridDim.x * WPC * G;
+    for (uint32_t pw = (blockIdx.x * WPC + wid) * G; pw < a.n_pair; pw += stride) {
+        const uint32_t pair = pw + grp;
+        if (pair >= a.n_pair) continue;                                  // whole group skips together
+        uint32_t pod, node;
+        if (a.dense) { pod = pair / a.n_node; node = pair - pod * a.n_node; }
+        else { pod = __ldg(&a.pair_pod[pair]); node = __ldg(&a.cand_nodes[pair]); }
+        if (node >= a.n_node) continue;                                   // unknown node: unsuitable
         const uint32_t c0 = __ldg(&a.pod_off[pod]);
         const uint32_t cnt = __ldg(&a.pod_off[pod + 1]) - c0;
         const uint32_t g0 = __ldg(&a.node_off[node]);
         const uint32_t ng = __ldg(&a.node_off[node + 1]) - g0;
         uint4 rec = make_uint4(0, 0, 0, 0);
-        if (lane < ng) rec = __ldg(&a.inv[g0 + lane]);
-        Lane L; L.load(rec, lane < ng);
+        if (gl < ng) rec = __ldg(&a.inv[g0 + gl]);
+        Lane L; L.load(rec, gl < ng);
         Dead D; FlagSink sink; GlobalGet get{a.claims + c0};
+        if (ng > W) sink.failed = true;                                   // cannot happen: W is chosen from the inventory
         uint32_t k = 0;
-        while (k < cnt && !sink.stop()) k += node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, true, a.sel);
-        if (!sink.failed && lane == 0) atomicOr(&a.bits[pair >> 5], 1u << (pair & 31));
+        while (k < cnt && !sink.stop()) k += node_step(L, D, lane, g0, tbl_s, get, k, cnt, sink, true, a.sel, gmask, gbase);
+        if (!sink.failed && gl == 0) atomicOr(&a.bits[pair >> 5], 1u << (pair & 31));
     }
 }
 

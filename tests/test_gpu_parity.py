@@ -242,3 +242,23 @@ def test_selectors_match_oracle(pkg, ctx, oracle, seed):
     finally:
         oracle.set_selectors()
         ctx.set_selectors(None); ctx.set_gpu_attrs(None)
+
+
+def test_unsuitable_dense_form_and_wide_nodes(pkg, ctx, oracle):
+    """Dense form (every pod x every node, no candidate arrays) == explicit lists; 8-, 16- and 32-lane groups."""
+    R = pkg.records
+    for width in (8, 13, 32):
+        g, off = R.make_inventory([width, 3, width, 0, 5], mig=True)
+        g["flags"][::3] = 0
+        w = pkg.synth.mixed(900, 5, 31 + width, invalid=False)
+        w.gpus, w.node_off = g, off
+        _, inv = oracle.allocate(g, off, w.table, w.claims[:200], w.out_off[:200], int(w.out_off[200]))
+        pod_off = np.arange(0, 901, 3, dtype=np.uint32)
+        n_pod = len(pod_off) - 1
+        ctx.set_table(w.table); ctx.set_inventory(inv, off)
+        dense = ctx.unsuitable(w.claims, pod_off)
+        cand_nodes = np.tile(np.arange(5, dtype=np.uint32), n_pod)
+        cand_off = (np.arange(n_pod + 1, dtype=np.uint32) * 5)
+        sparse = ctx.unsuitable(w.claims, pod_off, cand_nodes, cand_off)
+        ref = oracle.unsuitable(inv, off, w.table, w.claims, pod_off, cand_nodes, cand_off)
+        assert dense.tobytes() == ref.tobytes() and sparse.tobytes() == ref.tobytes(), width
