@@ -106,7 +106,7 @@ struct dra_ctx {
     bool ev_ok = false;
     float timings[5] = {0, 0, 0, 0, 0};
     uint32_t ev_mask = 0;
-    int hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0, fused_smem_set_stage = 0;
+    int hist8_smem_set = 0, hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0, fused_smem_set_stage = 0, fused_smem_set_cl = 0;
     uint64_t fused_max_work = 6000000ull;   // n_node * n_claim up to which the single-launch kernel is used
 
     ncclComm_t comm = nullptr;
@@ -169,13 +169,18 @@ int grow_pinned(dra_ctx* ctx, uint8_t*& p, size_t& cap, size_t need) {
     return DRA_OK;
 }
 
-struct Tiling { uint32_t T, n_tiles; };
-Tiling tiling(uint32_t n_claim) {
+struct Tiling { uint32_t T, n_tiles; bool cta_wide; };
+Tiling tiling(uint32_t n_claim, uint32_t n_node) {
+    // CTA-wide tiles of 2048 claims (k_bucket_hist8) whenever 8 x (n_node+1) u16 counters fit in shared memory
+    if ((size_t)8 * ((size_t)n_node + 2) * 2 <= 200 * 1024) {
+        uint32_t n_tiles = n_claim ? (n_claim + H8_TILE - 1) / H8_TILE : 1;
+        return {H8_TILE, n_tiles, true};
+    }
     uint32_t T = (n_claim + 63) / 64;
     T = (T + 31) & ~31u;
     T = std::max(256u, std::min(T, 65504u));
     uint32_t n_tiles = n_claim ? (n_claim + T - 1) / T : 1;
-    return {T, n_tiles};
+    return {T, n_tiles, false};
 }
 
 int ensure_batch(dra_ctx* ctx, uint32_t n_claim, uint32_t n_out, bool own_io) {
@@ -190,7 +195,7 @@ int ensure_batch(dra_ctx* ctx, uint32_t n_claim, uint32_t n_out, bool own_io) {
         ctx->cap_claims = ncap;
     }
     if (own_io) { int rc = grow(ctx, ctx->d_out, ctx->cap_out, need_o, 64); if (rc) return rc; }
-    Tiling t = tiling(n_claim);
+    Tiling t = tiling(n_claim, ctx->n_node);
     size_t need_h = (size_t)t.n_tiles * (ctx->n_node + 1);
     int rc = grow(ctx, ctx->d_hist, ctx->cap_hist, need_h, 64);
     return rc;
@@ -246,26 +251,43 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
                        (uint64_t)n_node * n_claim <= ctx->fused_max_work && fused_smem <= 225 * 1024 && n_node <= 16384;
     if (fused) {
         if (tail) { a.peer = *tail; if (tail_done) *tail_done = true; }
-        int& set = stage ? ctx->fused_smem_set_stage : ctx->fused_smem_set;
+        // clusters of 8 CTAs + TMA multicast when the array is staged and there are enough nodes to share it
+        constexpr int CLS = 8;
+        // Measured (profiles/cluster_multicast_r01e.txt): multicast cuts the filter phase 4.6K -> 4.0K cycles but
+        // the cluster launch + the two cluster barriers cost far more (28.1 vs 18.8 us per batch), so it stays an
+        // opt-in experiment (DRA_CLUSTER=1), not the default.
+        static const bool want_cluster = getenv("DRA_CLUSTER") != nullptr;
+        const bool cluster = stage && want_cluster && n_node + 1 >= (uint32_t)CLS;
+        int& set = cluster ? ctx->fused_smem_set_cl : (stage ? ctx->fused_smem_set_stage : ctx->fused_smem_set);
         if (fused_smem > 48 * 1024 && set < (int)fused_smem) {
-            if (stage) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-            else CU(cudaFuncSetAttribute(k_fused<FUSED_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            if (cluster) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            else if (stage) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            else CU(cudaFuncSetAttribute(k_fused<FUSED_NW, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
             set = (int)fused_smem;
         }
         a.claims = d_claims; a.out_off = d_out_off; a.n_claim = n_claim;
         if (getenv("DRA_TIMELINE")) {           // instrumentation only: per-CTA clock stamps of the last fused launch
-            if (ctx->tl_cap < (size_t)(n_node + 1) * 8) {
+            if (ctx->tl_cap < (size_t)(n_node + 16) * 8) {
                 if (ctx->d_timeline) CU(cudaFree(ctx->d_timeline));
-                ctx->tl_cap = (size_t)(n_node + 1) * 8 + 64;
+                ctx->tl_cap = (size_t)(n_node + 16) * 8 + 64;
                 CU(cudaMalloc((void**)&ctx->d_timeline, ctx->tl_cap * 8));
             }
             CU(cudaMemsetAsync(ctx->d_timeline, 0, ctx->tl_cap * 8, ctx->stream));
             a.timeline = ctx->d_timeline; ctx->tl_n = (n_node + 1) * 8;
         }
         prof.skip_to(3);
-        // grid = one CTA per node + one CTA for the claims that name no node
-        if (stage) k_fused<FUSED_NW, true><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
-        else k_fused<FUSED_NW, false><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
+        // grid = one CTA per node + one CTA for the claims that name no node (+ padding to whole clusters)
+        if (cluster) {
+            cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
+            lc.gridDim = dim3(((n_node + 1 + CLS - 1) / CLS) * CLS); lc.blockDim = dim3(FUSED_NW * 32);
+            lc.dynamicSmemBytes = fused_smem; lc.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, true, CLS>, a));
+        }
+        else if (stage) k_fused<FUSED_NW, true, 1><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
+        else k_fused<FUSED_NW, false, 1><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
         ctx->launches += 1;
         prof.mark();
         cudaError_t e = cudaGetLastError();
@@ -298,17 +320,30 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
             ctx->launches += 1;
             prof.mark(); prof.skip_to(3);
         } else {
-            Tiling t = tiling(n_claim);
-            size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
-            if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
-            if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
-                CU(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ctx->hist_smem_set = (int)smem;
+            Tiling t = tiling(n_claim, n_node);
+            if (t.cta_wide) {
+                const size_t smem = (size_t)8 * (((size_t)n_node + 2) & ~(size_t)1) * 2;
+                if (smem > 48 * 1024 && ctx->hist8_smem_set < (int)smem) {
+                    CU(cudaFuncSetAttribute(k_bucket_hist8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ctx->hist8_smem_set = (int)smem;
+                }
+                if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
+                k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank);
+                prof.mark();
+                k_bucket_scan8<<<(n_node + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8);
+                prof.mark();
+            } else {
+                size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
+                if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
+                if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
+                    CU(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ctx->hist_smem_set = (int)smem;
+                }
+                k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
+                prof.mark();
+                k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off);
+                prof.mark();
             }
-            k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
-            prof.mark();
-            k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off);
-            prof.mark();
             uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
             k_bucket_scatter<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
                                                               ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err);

@@ -454,6 +454,111 @@ k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node,
     if (tid == 0) claim_off[nb] = carry_s;
 }
 
+// ---- CTA-wide tiles (used whenever 8*(n_node+1) u16 counters fit in shared memory) ----------------------------
+// k_bucket_hist8: grid = n_tiles, 256 threads; tile = 2048 claims, warp w owns rows w*8 .. w*8+7 of it.
+// Per-warp counters keep the pass stable (as k_bucket_small); all 8 keys of a lane are loaded before the first
+// is used.  hist[t][n] = claims of tile t on node n; rank[i] = stable rank of claim i inside its tile.
+constexpr uint32_t H8_TILE = 2048;
+__global__ void __launch_bounds__(256)
+k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
+               uint32_t* __restrict__ hist, uint16_t* __restrict__ rank) {
+    extern __shared__ uint16_t cnt8[];                              // [8][nbp]
+    const uint32_t nb = n_node + 1, nbp = (nb + 1) & ~1u;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nbits = 32u - (uint32_t)__clz(n_node);
+    const uint32_t w0 = blockIdx.x * H8_TILE + wid * 256;
+    uint32_t keys[8];
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) { const uint32_t i = w0 + r * 32 + lane; keys[r] = i < n_claim ? __ldg(&claims[i]).y : 0xFFFFFFFFu; }
+    for (uint32_t i = tid; i < 4 * nbp; i += 256) reinterpret_cast<uint32_t*>(cnt8)[i] = 0;
+    __syncthreads();
+    uint16_t* mycnt = cnt8 + wid * nbp;
+    uint32_t local[8];
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = w0 + r * 32 + lane;
+        const bool act = i < n_claim;
+        const uint32_t key = act ? (keys[r] < n_node ? keys[r] : n_node) : 0xFFFFFFFFu;
+        keys[r] = key;
+        const uint32_t m = peers_by_bits(key, nbits, act);
+        const uint32_t rk = (uint32_t)__popc(m & lanemask_lt());
+        uint32_t old = 0;
+        if (act) old = mycnt[key];
+        local[r] = old + rk;
+        __syncwarp();
+        if (act && rk == 0) mycnt[key] = (uint16_t)(old + (uint32_t)__popc(m));
+        __syncwarp();
+    }
+    __syncthreads();
+    uint32_t* h = hist + (size_t)blockIdx.x * nb;
+    for (uint32_t n = tid; n < nb; n += 256) {
+        uint32_t run = 0;
+        #pragma unroll
+        for (uint32_t w = 0; w < 8; ++w) { const uint32_t v = cnt8[w * nbp + n]; cnt8[w * nbp + n] = (uint16_t)run; run += v; }
+        h[n] = run;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = w0 + r * 32 + lane;
+        if (i < n_claim) rank[i] = (uint16_t)(mycnt[keys[r]] + local[r]);
+    }
+}
+
+// k_bucket_scan8: grid = ceil((n_node+1)/256) CTAs, thread per node.  In place: hist[t][n] <- sum_{t'<t}; node totals
+// go to claim_off[n]; the LAST CTA to finish (ticket) turns the totals into the exclusive offsets.
+__global__ void __launch_bounds__(256)
+k_bucket_scan8(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node, uint32_t* __restrict__ claim_off,
+               uint32_t* __restrict__ ticket) {
+    const uint32_t nb = n_node + 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n = blockIdx.x * 256 + tid;
+    if (n < nb) {
+        uint32_t run = 0, t = 0;
+        for (; t + 8 <= n_tiles; t += 8) {
+            uint32_t v[8];
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = hist[(size_t)(t + q) * nb + n];
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) { hist[(size_t)(t + q) * nb + n] = run; run += v[q]; }
+        }
+        for (; t < n_tiles; ++t) { const uint32_t v = hist[(size_t)t * nb + n]; hist[(size_t)t * nb + n] = run; run += v; }
+        claim_off[n] = run;
+    }
+    __threadfence();
+    __shared__ uint32_t last_s, wsum[8], carry_s, total_s;
+    __syncthreads();
+    if (tid == 0) last_s = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last_s) return;
+    if (tid == 0) { *ticket = 0; carry_s = 0; }
+    __threadfence();
+    __syncthreads();
+    for (uint32_t n0 = 0; n0 < nb; n0 += 256) {
+        const uint32_t m = n0 + tid;
+        const uint32_t run = m < nb ? __ldcg(&claim_off[m]) : 0u;
+        uint32_t x = run;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, x, d); if (lane >= (uint32_t)d) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t w = lane < 8 ? wsum[lane] : 0u;
+            uint32_t ws = w;
+            #pragma unroll
+            for (int d = 1; d < 8; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, ws, d); if (lane >= (uint32_t)d) ws += y; }
+            if (lane < 8) wsum[lane] = ws - w;
+            if (lane == 7) total_s = ws;
+        }
+        __syncthreads();
+        const uint32_t excl = carry_s + wsum[wid] + (x - run);
+        if (m < nb) claim_off[m] = excl;
+        __syncthreads();
+        if (tid == 0) carry_s += total_s;
+        __syncthreads();
+    }
+    if (tid == 0) claim_off[nb] = carry_s;
+}
+
 // thread per claim.  sorted[dest] = claim with .y replaced by its first OutRec slot.
 // Claims that name no node (bucket n_node) get their INVALID record here and are not sorted in.
 __global__ void __launch_bounds__(256)
@@ -1075,11 +1180,16 @@ k_pack(const PackArgs a) {
 constexpr uint32_t FU_TBL = 0, FU_TBAR = 1024, FU_IBAR = 1032, FU_INV = 1040, FU_LIVE = 1552, FU_CNT = 2704, FU_LIST = 2832;   // counts: up to 32 warps
 constexpr uint32_t FU_PIECE = 256;          // claims per staged piece (4 KiB bulk copy, own mbarrier)
 constexpr uint32_t FU_MAXPIECE = 8;         // pieces per warp part => staging needs n_claim <= NW * 2048
-__host__ __device__ constexpr size_t fused_list_bytes(uint32_t n_claim, int nw) {
-    return ((size_t)((n_claim + nw * 32 - 1) / (nw * 32)) * 32 * nw) * 4;
+// per-warp part of the claim array: a multiple of 32 claims, of a whole piece when the array is staged
+__host__ __device__ constexpr uint32_t fused_chunk(uint32_t n_claim, int nw, bool stage) {
+    return stage ? ((n_claim + nw * FU_PIECE - 1) / (nw * FU_PIECE)) * FU_PIECE
+                 : ((n_claim + nw * 32 - 1) / (nw * 32)) * 32;
+}
+__host__ __device__ constexpr size_t fused_list_bytes(uint32_t n_claim, int nw, bool stage) {
+    return (size_t)fused_chunk(n_claim, nw, stage) * nw * 4;
 }
 __host__ __device__ constexpr size_t fused_smem_bytes(uint32_t n_claim, int nw, bool stage) {
-    return FU_LIST + (stage ? (size_t)nw * FU_MAXPIECE * 8 : 0) + fused_list_bytes(n_claim, nw) + 16 + (stage ? (size_t)n_claim * 16 + 16 : 0);
+    return FU_LIST + (stage ? (size_t)nw * FU_MAXPIECE * 8 : 0) + fused_list_bytes(n_claim, nw, stage) + 16 + (stage ? (size_t)n_claim * 16 + 16 : 0);
 }
 
 template <int NW>
@@ -1108,19 +1218,32 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #define DRA_STAMP(k) do { if (a.timeline && threadIdx.x == 0) a.timeline[blockIdx.x * 8 + (k)] = (k) == 0 ? globaltimer_ns() : (unsigned long long)clock64(); } while (0)
 
-template <int NW, bool STAGE>
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 1-D TMA bulk copy global -> the same shared-memory offset of every CTA of the cluster named in `mask`; each
+// destination CTA's mbarrier (same offset) receives the complete_tx.  One L2 read feeds all of them.
+__device__ __forceinline__ void tma_load_multicast(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+
+// CL = thread-block cluster size (1 or 8).  With CL = 8 the staged claim array is fetched from L2 ONCE per
+// cluster: CTA r of the cluster loads pieces r, r+8, ... and TMA-multicasts each into all 8 CTAs.
+template <int NW, bool STAGE, int CL>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_fused(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
+    static_assert(CL == 1 || STAGE, "clusters only make sense with the staged claim array");
     DRA_STAMP(0); DRA_STAMP(1);
     const uint32_t sbase = smem_base(dyn_smem);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t node = blockIdx.x;
-    const bool has_node = node < a.n_node;       // the extra CTA (blockIdx == n_node) handles claims that name no node
+    const bool has_node = node < a.n_node;       // CTA n_node handles claims that name no node; later CTAs pad the cluster
     const uint32_t tbar = sbase + FU_TBAR, ibar = sbase + FU_IBAR;
     const uint32_t list_addr = sbase + FU_LIST + (STAGE ? (uint32_t)NW * FU_MAXPIECE * 8u : 0u);
-    const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(a.n_claim, NW) + 15u) & ~15u) : 0u;
-    const uint32_t sbar = sbase + FU_LIST;       // STAGE: NW x FU_MAXPIECE piece barriers
+    const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(a.n_claim, NW, STAGE) + 15u) & ~15u) : 0u;
+    const uint32_t sbar = sbase + FU_LIST;       // STAGE: one mbarrier per 4 KiB piece of the claim array
 
     // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
     uint32_t g0 = 0, g1 = 0;
@@ -1133,17 +1256,33 @@ k_fused(const PackArgs a) {
     }
     const uint32_t ng = g1 - g0;
     if (threadIdx.x == 0 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
-    if (STAGE) __syncthreads();                    // piece barriers are initialised before any warp arms them
+    if (STAGE) {
+        __syncthreads();                           // piece barriers are initialised ...
+        if (CL > 1) { cluster_arrive(); cluster_wait(); }      // ... in every CTA of the cluster before any multicast
+        // warp 0 arms every piece barrier of THIS CTA and issues the pieces this CTA is responsible for
+        const uint32_t npt = (a.n_claim + FU_PIECE - 1) / FU_PIECE;
+        const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+        if (wid == 0)
+            for (uint32_t g = lane; g < npt; g += 32) {
+                const uint32_t c0 = g * FU_PIECE, bytes = min(FU_PIECE, a.n_claim - c0) * 16u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar + g * 8), "r"(bytes) : "memory");
+                if (g % CL == crank) {
+                    if (CL > 1) tma_load_multicast(stage_addr + (c0 << 4), a.claims + c0, bytes, sbar + g * 8, (uint16_t)((1u << CL) - 1u));
+                    else asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                      ::"r"(stage_addr + (c0 << 4)), "l"(a.claims + c0), "r"(bytes), "r"(sbar + g * 8) : "memory");
+                }
+            }
+    }
     DRA_STAMP(2);
 
     // ---- filter: which claims select this node (all warps) ------------------------------------------
-    const uint32_t chunk = ((a.n_claim + NW * 32 - 1) / (NW * 32)) * 32;      // per-warp part, multiple of 32
+    const uint32_t chunk = fused_chunk(a.n_claim, NW, STAGE);          // per-warp part
     const uint32_t lo = wid * chunk, hi = min(a.n_claim, lo + chunk);
     const uint32_t ltmask = lanemask_lt();
     const uint32_t my_list = list_addr + (lo << 2);
     const uint32_t want = has_node ? node : 0xFFFFFFFEu;
     uint32_t cntw = 0;
-    if (!has_node) {
+    if (node == a.n_node) {
         // claims that name no node of the inventory: INVALID (spec §3); no state is touched
         for (uint32_t i = threadIdx.x; i < a.n_claim; i += NW * 32) {
             const uint4 c = __ldg(&a.claims[i]);
@@ -1168,16 +1307,12 @@ k_fused(const PackArgs a) {
     };
     constexpr int U = 8;
     if (STAGE) {
-        // the warp's whole part goes out as 4 KiB TMA bulk copies, all in flight at once; pieces are scanned
-        // from shared memory as they land, and the pack phase later reads the claims from the same copy
+        // the whole array is in flight as 4 KiB TMA bulk copies (issued above); each warp scans the pieces of its
+        // part from shared memory as they land, and the pack phase later reads the claims from the same copy
         const uint32_t npiece = hi > lo ? (hi - lo + FU_PIECE - 1) / FU_PIECE : 0;
-        if (lane == 0)
-            for (uint32_t q = 0; q < npiece; ++q) {
-                const uint32_t c0 = lo + q * FU_PIECE, n = min(FU_PIECE, hi - c0);
-                tma_load_a(stage_addr + (c0 << 4), a.claims + c0, n * 16u, sbar + (wid * FU_MAXPIECE + q) * 8);
-            }
+        const uint32_t g_first = lo / FU_PIECE;                         // parts are whole pieces (fused_chunk)
         for (uint32_t q = 0; q < npiece; ++q) {
-            mbar_wait_a(sbar + (wid * FU_MAXPIECE + q) * 8, 0);
+            mbar_wait_a(sbar + (g_first + q) * 8, 0);
             uint32_t kv[U];
             #pragma unroll
             for (int u = 0; u < U; ++u) {                      // all 8 shared loads in flight before the first test
@@ -1207,6 +1342,7 @@ k_fused(const PackArgs a) {
     DRA_STAMP(3);
     if (lane == 0) sts32(sbase + FU_CNT + (wid << 2), cntw);
     __syncthreads();
+    if (CL > 1) cluster_arrive();                  // this CTA has received every piece; matched by the wait at the end
     DRA_STAMP(4);
 
     IdxGet<NW> get;
@@ -1261,6 +1397,7 @@ k_fused(const PackArgs a) {
             }
         }
     }
+    if (CL > 1) cluster_wait();                    // nobody leaves while a cluster peer may still be receiving multicasts
     if (a.peer.world == 0) return;
 
     // ---- multi-GPU tail: all-gather by peer stores, fused here (no extra launch) -------------------------
