@@ -158,7 +158,8 @@ typedef struct dra_cfg {
     uint32_t flags;         /* DRA_CFG_* */
 } dra_cfg;
 
-#define DRA_CFG_USE_GRAPH  0x1u  /* replay the kernel chain as one CUDA graph (host-buffer calls) */
+#define DRA_CFG_USE_GRAPH  0x1u  /* dra_allocate_batch: replay H2D -> kernels -> D2H as ONE CUDA graph launch when a
+                                    call repeats the previous call's buffers and sizes (captured on the 2nd such call) */
 #define DRA_CFG_NO_FUSED   0x2u  /* never take the single-launch path (always bucket + pack); for tests */
 
 /* error codes (negative) */

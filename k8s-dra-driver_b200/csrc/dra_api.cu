@@ -112,6 +112,14 @@ struct dra_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
 
+    // CUDA-graph replay of the host-buffer Allocate call
+    struct GraphKeyT { const void* c; const void* o; void* d; uint32_t n_claim, n_out, flags; uint64_t epoch;
+                       bool operator==(const GraphKeyT& k) const { return c == k.c && o == k.o && d == k.d && n_claim == k.n_claim && n_out == k.n_out && flags == k.flags && epoch == k.epoch && c != nullptr; } };
+    GraphKeyT graph_key{};
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_launches = 0;
+    uint64_t state_epoch = 1;     // bumped by every call that reallocates or re-points device state
+
     // peer-memory all-gather
     bool peer_ready = false;
     uint32_t peer_n_per = 0, peer_epoch = 0;
@@ -125,6 +133,8 @@ struct dra_ctx {
 
     std::string err;
 };
+
+using GraphKey = dra_ctx::GraphKeyT;
 
 namespace {
 
@@ -147,6 +157,7 @@ int grow(dra_ctx* ctx, T*& p, size_t& cap, size_t need, size_t slack = 16) {
     p = nullptr;
     CU(cudaMalloc((void**)&p, ncap * sizeof(T)));
     cap = ncap;
+    ctx->state_epoch++;
     return DRA_OK;
 }
 
@@ -156,6 +167,7 @@ int grow_nc(dra_ctx* ctx, T*& p, size_t have_cap, size_t new_cap) {   // compani
     if (p) CU(cudaFree(p));
     p = nullptr;
     CU(cudaMalloc((void**)&p, new_cap * sizeof(T)));
+    ctx->state_epoch++;
     return DRA_OK;
 }
 
@@ -428,6 +440,8 @@ int dra_ctx_create(const dra_cfg* cfg, dra_ctx** out) {
     c->h_err = (volatile uint32_t*)he;
     for (uint32_t i = 0; i < ERR_WORDS; ++i) c->h_err[i] = 0;
     if (cudaHostGetDevicePointer((void**)&c->h_err_dev, he, 0) != cudaSuccess) return bail(fail(c, DRA_E_CUDA, "cudaHostGetDevicePointer"));
+    if (cudaMalloc((void**)&c->d_ticket, 64) != cudaSuccess) return bail(fail(c, DRA_E_NOMEM, "cudaMalloc ticket"));
+    cudaMemset(c->d_ticket, 0, 64);
     for (int i = 0; i < 8; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(fail(c, DRA_E_CUDA, "cudaEventCreate"));
     c->ev_ok = true;
     if (cfg->max_claims) { int rc = ensure_batch(c, cfg->max_claims, cfg->max_claims, true); if (rc) return bail(rc); }
@@ -439,6 +453,7 @@ void dra_ctx_destroy(dra_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->comm) { std::lock_guard<std::mutex> lk(g_nccl_mu); if (g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm); }
     for (int r = 0; r < (int)PEER_MAX; ++r) if (c->peer_base[r] && c->peer_base[r] != c->peer_local) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->peer_local) cudaFree(c->peer_local);
@@ -467,6 +482,7 @@ int dra_set_placement_table(dra_ctx* ctx, uint32_t model, const dra_profile_tbl*
     }
     ctx->h_tbl[model] = *tbl;
     ctx->tbl_dirty = true;
+    ctx->state_epoch++;
     return DRA_OK;
 }
 
@@ -501,6 +517,7 @@ int dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu, con
     if (n_gpu) CU(cudaMemcpy(ctx->d_inv_live, gpus, (size_t)n_gpu * 16, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_node_off, node_off, ((size_t)n_node + 1) * 4, cudaMemcpyHostToDevice));
     ctx->n_gpu = n_gpu; ctx->n_node = n_node;
+    ctx->state_epoch++;
     ctx->max_width = 0;
     for (uint32_t n = 0; n < n_node; ++n) ctx->max_width = std::max(ctx->max_width, node_off[n + 1] - node_off[n]);
     ctx->cap_hist = 0;  // histogram geometry depends on n_node
@@ -519,6 +536,7 @@ int dra_set_gpu_attrs(dra_ctx* ctx, const dra_gpu_attr* attrs, uint32_t n_gpu) {
     CU(cudaMalloc((void**)&ctx->d_attrs, (size_t)n_gpu * 16 + 64));
     CU(cudaMemcpy(ctx->d_attrs, attrs, (size_t)n_gpu * 16, cudaMemcpyHostToDevice));
     ctx->n_attr = n_gpu;
+    ctx->state_epoch++;
     return DRA_OK;
 }
 
@@ -532,6 +550,7 @@ int dra_set_selectors(dra_ctx* ctx, const dra_selector* sels, uint32_t n_sel) {
     CU(cudaMalloc((void**)&ctx->d_sels, (size_t)n_sel * 64 + 64));
     CU(cudaMemcpy(ctx->d_sels, sels, (size_t)n_sel * 64, cudaMemcpyHostToDevice));
     ctx->n_sel = n_sel;
+    ctx->state_epoch++;
     return DRA_OK;
 }
 
@@ -587,13 +606,47 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
         if ((rc = grow_pinned(ctx, ctx->h_in, ctx->h_in_cap, ob))) return rc;
         memcpy(ctx->h_in, out_off, ob); src_o = ctx->h_in;
     }
-    if (cb) CU(cudaMemcpyAsync(ctx->d_claims, src_c, cb, cudaMemcpyHostToDevice, ctx->stream));
-    if (ob) CU(cudaMemcpyAsync(ctx->d_out_off, src_o, ob, cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_allocate(ctx, ctx->d_claims, n_claim, out_off ? ctx->d_out_off : nullptr, ctx->d_out, n_out, flags);
-    if (rc) return rc;
     const bool direct = rb && is_pinned(out, rb);
     if (rb && !direct && (rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, rb))) return rc;
-    if (rb) CU(cudaMemcpyAsync(direct ? (void*)out : (void*)ctx->h_out, ctx->d_out, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    void* dst_o = direct ? (void*)out : (void*)ctx->h_out;
+
+    // DRA_CFG_USE_GRAPH: H2D -> kernel chain -> D2H replayed as ONE cudaGraphLaunch when the call has the same
+    // shape and buffers as the previous one (the first call of a shape runs eagerly: it also sets the kernels'
+    // shared-memory attributes, which cannot happen inside a capture).
+    GraphKey key{src_c, src_o, dst_o, n_claim, n_out, flags, ctx->state_epoch};
+    const bool want_graph = (ctx->cfg_flags & DRA_CFG_USE_GRAPH) && !ctx->profiling && !getenv("DRA_TIMELINE");
+    if (want_graph && ctx->graph_exec && key == ctx->graph_key) {
+        CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        ctx->launches += ctx->graph_launches;
+    } else {
+        const bool capture = want_graph && key == ctx->graph_key;      // second call of this shape: capture it
+        if (want_graph && !capture) { ctx->graph_key = key; if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; } }
+        const uint64_t l0 = ctx->launches;
+        if (capture) CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t ce = cudaSuccess;
+        if (cb) ce = cudaMemcpyAsync(ctx->d_claims, src_c, cb, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess && ob) ce = cudaMemcpyAsync(ctx->d_out_off, src_o, ob, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) rc = launch_allocate(ctx, ctx->d_claims, n_claim, out_off ? ctx->d_out_off : nullptr, ctx->d_out, n_out, flags);
+        if (ce == cudaSuccess && rc == DRA_OK && rb) ce = cudaMemcpyAsync(dst_o, ctx->d_out, rb, cudaMemcpyDeviceToHost, ctx->stream);
+        if (capture) {
+            cudaGraph_t g = nullptr;
+            cudaError_t ee = cudaStreamEndCapture(ctx->stream, &g);
+            if (ce != cudaSuccess || rc != DRA_OK || ee != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                (void)cudaGetLastError();
+                ctx->graph_key = GraphKey{};
+                return rc != DRA_OK ? rc : fail(ctx, DRA_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+            }
+            ctx->graph_launches = (uint32_t)(ctx->launches - l0);
+            cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { ctx->graph_exec = nullptr; return fail(ctx, DRA_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+            CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        } else {
+            if (ce != cudaSuccess) return fail(ctx, DRA_E_CUDA, "enqueue: %s", cudaGetErrorString(ce));
+            if (rc) return rc;
+        }
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     collect_timings(ctx, 4);
     if ((rc = check_err(ctx))) return rc;

@@ -262,3 +262,42 @@ def test_unsuitable_dense_form_and_wide_nodes(pkg, ctx, oracle):
         sparse = ctx.unsuitable(w.claims, pod_off, cand_nodes, cand_off)
         ref = oracle.unsuitable(inv, off, w.table, w.claims, pod_off, cand_nodes, cand_off)
         assert dense.tobytes() == ref.tobytes() and sparse.tobytes() == ref.tobytes(), width
+
+
+def test_cuda_graph_replay_of_the_host_call(pkg, oracle):
+    """DRA_CFG_USE_GRAPH: the 2nd call of a shape is captured, later calls replay one graph; results must not
+    depend on whether a call ran eagerly, was captured, or was replayed — including after the buffers' CONTENT
+    changes and after the shape changes."""
+    R = pkg.records
+    w = pkg.synth.cfg2(3000, 40)
+    ref, _ = oracle.allocate(w.gpus, w.node_off, w.table, w.claims)
+    with pkg.api.Context(device=0, flags=pkg.api.CFG_USE_GRAPH) as g:
+        g.set_table(w.table); g.set_inventory(w.gpus, w.node_off)
+        pc = pkg.api.PinnedBuffer(w.n_claim, R.CLAIM_DTYPE); pc.array[:] = w.claims
+        po = pkg.api.PinnedBuffer(w.n_out, R.OUT_DTYPE)
+        F = pkg.api.F_FRESH_INVENTORY
+        for it in range(5):                                   # eager, capture, replay, replay, replay
+            po.array[:] = 0
+            l0 = g.launch_count()
+            g.allocate(pc.array, None, w.n_out, flags=F, out=po.array)
+            assert po.array.tobytes() == ref.tobytes(), it
+            assert g.launch_count() - l0 == 1
+        # same buffers, new content: the graph reads what is there now
+        w2 = pkg.synth.cfg2(3000, 40, seed_off=77)
+        pc.array[:] = w2.claims
+        ref2, _ = oracle.allocate(w.gpus, w.node_off, w.table, w2.claims)
+        g.allocate(pc.array, None, w.n_out, flags=F, out=po.array)
+        assert po.array.tobytes() == ref2.tobytes()
+        # without FRESH the live inventory carries over between replays too
+        g.reset_inventory()
+        a = g.allocate(pc.array, None, w.n_out, flags=0, out=po.array).copy()
+        b = g.allocate(pc.array, None, w.n_out, flags=0, out=po.array).copy()
+        r1, inv1 = oracle.allocate(w.gpus, w.node_off, w.table, w2.claims)
+        r2, _ = oracle.allocate(inv1, w.node_off, w.table, w2.claims)
+        assert a.tobytes() == r1.tobytes() and b.tobytes() == r2.tobytes()
+        # a different shape falls back to eager, then gets its own graph
+        g.set_inventory(w.gpus, w.node_off)
+        out = g.allocate(w.claims[:1000].copy())
+        r3, _ = oracle.allocate(w.gpus, w.node_off, w.table, w.claims[:1000])
+        assert out.tobytes() == r3.tobytes()
+        pc.free(); po.free()
