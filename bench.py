@@ -314,7 +314,7 @@ def run_ours(args):
 
     def step_e2e():
         if world == 1:
-            ctx.allocate(pin_c.array, None, n_out, flags=F, out=pin_o.array)
+            ctx.allocate_raw(pin_c.ptr, n_claim, None, pin_o.ptr, n_out, F)      # the bare C-ABI call
         else:
             d_claims.copy_(h_claims_t, non_blocking=True)
             step_dev()

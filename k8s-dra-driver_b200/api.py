@@ -215,6 +215,14 @@ class Context:
         self._check(self._lib.dra_allocate_batch(self._h, _ptr(c), len(c), _ptr(oo), _ptr(out), n_out, flags))
         return out
 
+    def allocate_raw(self, claims_ptr: int, n_claim: int, out_off_ptr: int | None, out_ptr: int, n_out: int,
+                     flags: int = 0) -> None:
+        """dra_allocate_batch on raw HOST addresses (e.g. PinnedBuffer.ptr): the bare C-ABI call, without the
+        numpy conveniences of allocate() — what a cgo caller pays."""
+        rc = self._lib.dra_allocate_batch(self._h, claims_ptr, n_claim, out_off_ptr, out_ptr, n_out, flags)
+        if rc != OK:
+            self._check(rc)
+
     def allocate_device(self, d_claims: int, n_claim: int, d_out_off: int | None, d_out: int, n_out: int,
                         flags: int = 0):
         """Device pointers (ints); enqueues on the context's stream, no synchronisation."""
