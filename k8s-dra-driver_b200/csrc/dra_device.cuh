@@ -1259,11 +1259,12 @@ k_fused(const PackArgs a) {
     if (STAGE) {
         __syncthreads();                           // piece barriers are initialised ...
         if (CL > 1) { cluster_arrive(); cluster_wait(); }      // ... in every CTA of the cluster before any multicast
-        // warp 0 arms every piece barrier of THIS CTA and issues the pieces this CTA is responsible for
+        // every warp arms (and, for the pieces this CTA is responsible for, issues) its share of the pieces:
+        // TMA issues from one warp serialise (~100 cycles each), so they are spread over the 8 warps' lane 0
         const uint32_t npt = (a.n_claim + FU_PIECE - 1) / FU_PIECE;
         const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-        if (wid == 0)
-            for (uint32_t g = lane; g < npt; g += 32) {
+        if (lane == 0)
+            for (uint32_t g = wid; g < npt; g += NW) {
                 const uint32_t c0 = g * FU_PIECE, bytes = min(FU_PIECE, a.n_claim - c0) * 16u;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar + g * 8), "r"(bytes) : "memory");
                 if (g % CL == crank) {
