@@ -264,6 +264,16 @@ int  dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec);
 int  dra_peer_export(dra_ctx* ctx, uint32_t n_per_rank, void* handle64);
 int  dra_peer_import(dra_ctx* ctx, const void* handles);
 
+/* ---- adjacent integer searches of the reference, batched (API completeness) -------------- */
+
+/* limit.Megabyte() over n quantities (api/nvidia.com/resource/gpu/v1alpha1/sharing.go:234-237):
+ * mib[i] = bytes[i]/1024/1024 truncated toward zero, valid[i] = mib[i] > 0. */
+int  dra_mps_limits_batch(dra_ctx* ctx, const int64_t* bytes, uint32_t n, int64_t* mib, uint8_t* valid);
+/* imexDomainOffsets.add's search over n_dom domains (cmd/nvidia-dra-controller/imex.go:336-349): used offsets of
+ * domain d are used[dom_off[d] .. dom_off[d+1]); out[d] = lowest multiple of step below limit not in them, -1 if none. */
+int  dra_imex_offsets_batch(dra_ctx* ctx, const int32_t* used, const uint32_t* dom_off, uint32_t n_dom,
+                            int32_t step, int32_t limit, int32_t* out);
+
 /* ---- host memory + instrumentation ---------------------------------------------------------------- */
 
 /* Page-locked host buffers: passing these to the *_batch calls skips the internal staging copy. */

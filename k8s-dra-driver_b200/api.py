@@ -55,6 +55,8 @@ SYMBOLS = {
     "dra_gather_read": (_i32, [_vp, _vp, _u32]),
     "dra_peer_export": (_i32, [_vp, _u32, _vp]),
     "dra_peer_import": (_i32, [_vp, _vp]),
+    "dra_mps_limits_batch": (_i32, [_vp, _vp, _u32, _vp, _vp]),
+    "dra_imex_offsets_batch": (_i32, [_vp, _vp, _vp, _u32, C.c_int32, C.c_int32, _vp]),
     "dra_host_alloc": (_vp, [C.c_size_t]),
     "dra_host_free": (None, [_vp]),
     "dra_launch_count": (_u64, [_vp]),
@@ -257,6 +259,21 @@ class Context:
         o = np.ascontiguousarray(out, dtype=R.OUT_DTYPE)
         oo = None if out_off is None else np.ascontiguousarray(out_off, dtype=np.uint32)
         self._check(self._lib.dra_deallocate_batch(self._h, _ptr(c), len(c), _ptr(oo), _ptr(o), len(o)))
+
+    # -- adjacent integer searches ------------------------------------------------------------------------
+    def mps_limits(self, nbytes) -> tuple:
+        b = np.ascontiguousarray(nbytes, dtype=np.int64)
+        mib = np.zeros(len(b), dtype=np.int64); valid = np.zeros(len(b), dtype=np.uint8)
+        self._check(self._lib.dra_mps_limits_batch(self._h, _ptr(b), len(b), _ptr(mib), _ptr(valid)))
+        return mib, valid.astype(bool)
+
+    def imex_offsets(self, used_lists, step: int = 128, limit: int = 2048) -> np.ndarray:
+        off = np.zeros(len(used_lists) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(u) for u in used_lists])
+        used = np.ascontiguousarray(np.concatenate([np.asarray(u, dtype=np.int32) for u in used_lists]) if len(used_lists) and off[-1] else np.zeros(1, np.int32), dtype=np.int32)
+        out = np.zeros(len(used_lists), dtype=np.int32)
+        self._check(self._lib.dra_imex_offsets_batch(self._h, _ptr(used), _ptr(off), len(used_lists), step, limit, _ptr(out)))
+        return out
 
     # -- multi-GPU ------------------------------------------------------------------------------------
     @staticmethod

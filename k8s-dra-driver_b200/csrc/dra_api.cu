@@ -925,6 +925,44 @@ int dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec) {
     return DRA_OK;
 }
 
+// ---- adjacent integer searches, batched ------------------------------------------------
+int dra_mps_limits_batch(dra_ctx* ctx, const int64_t* bytes, uint32_t n, int64_t* mib, uint8_t* valid) {
+    if (!ctx || (n && (!bytes || !mib || !valid))) return DRA_E_INVAL;
+    if (!n) return DRA_OK;
+    CU(cudaSetDevice(ctx->device));
+    void *d_b = nullptr, *d_m = nullptr, *d_v = nullptr;
+    CU(cudaMalloc(&d_b, (size_t)n * 8)); CU(cudaMalloc(&d_m, (size_t)n * 8)); CU(cudaMalloc(&d_v, n));
+    cudaError_t e = cudaMemcpyAsync(d_b, bytes, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    k_mps_limits<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*)d_b, n, (long long*)d_m, (uint8_t*)d_v);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mib, d_m, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(valid, d_v, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_b); cudaFree(d_m); cudaFree(d_v);
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "dra_mps_limits_batch: %s", cudaGetErrorString(e));
+    return DRA_OK;
+}
+
+int dra_imex_offsets_batch(dra_ctx* ctx, const int32_t* used, const uint32_t* dom_off, uint32_t n_dom, int32_t step, int32_t limit, int32_t* out) {
+    if (!ctx || !dom_off || (n_dom && !out) || step <= 0 || limit < 0) return DRA_E_INVAL;
+    if (!n_dom) return DRA_OK;
+    const uint32_t n_used = dom_off[n_dom];
+    if (n_used && !used) return DRA_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    void *d_u = nullptr, *d_o = nullptr, *d_r = nullptr;
+    CU(cudaMalloc(&d_u, (size_t)n_used * 4 + 16)); CU(cudaMalloc(&d_o, ((size_t)n_dom + 1) * 4)); CU(cudaMalloc(&d_r, (size_t)n_dom * 4));
+    cudaError_t e = cudaSuccess;
+    if (n_used) e = cudaMemcpyAsync(d_u, used, (size_t)n_used * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, dom_off, ((size_t)n_dom + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    k_imex_offsets<<<(n_dom + 7) / 8, 256, 0, ctx->stream>>>((const int*)d_u, (const uint32_t*)d_o, n_dom, step, limit, (int*)d_r);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_r, (size_t)n_dom * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_u); cudaFree(d_o); cudaFree(d_r);
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "dra_imex_offsets_batch: %s", cudaGetErrorString(e));
+    return DRA_OK;
+}
+
 // ---- host memory + instrumentation -----------------------------------------------------------------
 
 void* dra_host_alloc(size_t bytes) {

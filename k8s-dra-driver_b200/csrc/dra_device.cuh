@@ -1248,17 +1248,16 @@ k_fused(const PackArgs a) {
     // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
     uint32_t g0 = 0, g1 = 0;
     if (has_node) { g0 = __ldg(&a.node_off[node]); g1 = __ldg(&a.node_off[node + 1]); }
-    if (threadIdx.x == 0) {
-        mbar_init_a(tbar, 1); mbar_init_a(ibar, 1);
-        if (STAGE) for (uint32_t q = 0; q < NW * FU_MAXPIECE; ++q) mbar_init_a(sbar + q * 8, 1);
-        mbar_fence_init();
-        tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
-    }
+    // barrier init spread over the threads (one mbarrier.init each), then one fence + sync
+    if (threadIdx.x == 0) { mbar_init_a(tbar, 1); mbar_init_a(ibar, 1); }
+    if (STAGE) { const uint32_t npt_ = (a.n_claim + FU_PIECE - 1) / FU_PIECE; if (threadIdx.x < npt_) mbar_init_a(sbar + threadIdx.x * 8, 1); }
+    mbar_fence_init();
+    __syncthreads();
+    if (threadIdx.x == 0) tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
     const uint32_t ng = g1 - g0;
-    if (threadIdx.x == 0 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
+    if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
     if (STAGE) {
-        __syncthreads();                           // piece barriers are initialised ...
-        if (CL > 1) { cluster_arrive(); cluster_wait(); }      // ... in every CTA of the cluster before any multicast
+        if (CL > 1) { cluster_arrive(); cluster_wait(); }      // barriers initialised in every CTA of the cluster before any multicast
         // every warp arms (and, for the pieces this CTA is responsible for, issues) its share of the pieces:
         // TMA issues from one warp serialise (~100 cycles each), so they are spread over the 8 warps' lane 0
         const uint32_t npt = (a.n_claim + FU_PIECE - 1) / FU_PIECE;
@@ -1592,6 +1591,40 @@ k_peer_wait(const PeerArgs a, uint4* __restrict__ user_out) {
     const uint4* src = a.buf[a.rank] + (size_t)a.parity * a.world * a.n_per16;
     const uint32_t n = a.world * a.n_per16, stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) user_out[i] = src[i];
+}
+
+
+// ====================================================================================================
+// adjacent integer searches of the reference, batched (API completeness)
+// ====================================================================================================
+// limit.Megabyte() — api/nvidia.com/resource/gpu/v1alpha1/sharing.go:234-237: v = bytes/1024/1024 truncated toward
+// zero (Go and C agree), valid iff v > 0.
+__global__ void __launch_bounds__(256)
+k_mps_limits(const long long* __restrict__ bytes, uint32_t n, long long* __restrict__ mib, uint8_t* __restrict__ valid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long v = bytes[i] / 1024 / 1024;
+    mib[i] = v; valid[i] = v > 0 ? 1 : 0;
+}
+
+// imexDomainOffsets.add's search — cmd/nvidia-dra-controller/imex.go:336-349: lowest multiple of `step` below
+// `limit` that is not in the domain's used list; -1 = "channel limit reached".  One warp per domain, lane = candidate
+// window (limit/step <= 32 in the reference: 2048/128 = 16); wider ranges loop.
+__global__ void __launch_bounds__(256)
+k_imex_offsets(const int* __restrict__ used, const uint32_t* __restrict__ dom_off, uint32_t n_dom, int step, int limit,
+               int* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31, dom = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (dom >= n_dom) return;
+    const uint32_t u0 = dom_off[dom], u1 = dom_off[dom + 1];
+    int found = -1;
+    for (int base = 0; base < limit && found < 0; base += 32 * step) {
+        const int off = base + (int)lane * step;
+        bool taken = off >= limit;
+        for (uint32_t k = u0; k < u1 && !taken; ++k) taken = used[k] == off;
+        const uint32_t freeb = __ballot_sync(FULLMASK, !taken);
+        if (freeb) found = base + ((int)__ffs(freeb) - 1) * step;
+    }
+    if (lane == 0) out[dom] = found;
 }
 
 }  // namespace dra

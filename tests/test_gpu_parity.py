@@ -301,3 +301,21 @@ def test_cuda_graph_replay_of_the_host_call(pkg, oracle):
         r3, _ = oracle.allocate(w.gpus, w.node_off, w.table, w.claims[:1000])
         assert out.tobytes() == r3.tobytes()
         pc.free(); po.free()
+
+
+def test_adjacent_integer_searches(pkg, ctx, oracle):
+    """limit.Megabyte (sharing.go:234-237, vectors of sharing_test.go) and the IMEX offset search
+    (imex.go:336-349) as batch kernels, against the oracle's restatements."""
+    q = pkg.sharing.quantity_value
+    vals = [q(x) for x in ("2Gi", "1Gi", "10Mi", "10M", "1G", "1M", "0", "1048575", "1048576")] + [-5 * 2 ** 20, 2 ** 50 + 123]
+    mib, valid = ctx.mps_limits(vals)
+    for v, m, ok in zip(vals, mib, valid):
+        assert (int(m), bool(ok)) == oracle.megabyte(v)
+    assert list(mib[:6]) == [2048, 1024, 10, 9, 953, 0] and list(valid[:6]) == [True] * 5 + [False]
+    rng = np.random.default_rng(3)
+    doms = [[], [0], [0, 128, 384], list(range(0, 2048, 128)), [128, 256], list(range(0, 2048, 128))[:-1]]
+    doms += [sorted(rng.choice(np.arange(0, 2048, 128), size=int(rng.integers(0, 16)), replace=False).tolist()) for _ in range(50)]
+    got = ctx.imex_offsets(doms)
+    assert list(got) == [oracle.imex_offset(d) for d in doms]
+    wide = ctx.imex_offsets([list(range(0, 64 * 10, 10))], step=10, limit=1000)      # more than 32 windows
+    assert wide[0] == oracle.imex_offset(list(range(0, 640, 10)), step=10, limit=1000) == 640
