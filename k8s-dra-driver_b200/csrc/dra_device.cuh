@@ -1588,6 +1588,7 @@ k_peer_wait(const PeerArgs a, uint4* __restrict__ user_out) {
         if (!ok) a.err.set(ERR_PEER_TIMEOUT);
     }
     __syncthreads();
+    if (!user_out) return;                         // the table stays in the IPC buffer (dra_gather_table)
     const uint4* src = a.buf[a.rank] + (size_t)a.parity * a.world * a.n_per16;
     const uint32_t n = a.world * a.n_per16, stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) user_out[i] = src[i];
