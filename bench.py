@@ -163,7 +163,7 @@ def run_reference(args):
     n = CLAIMS_PER_RANK * world
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / rate, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u16/u32 integer", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": config(world),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": th, "kind": "port",
                              "sample": f"{reps} full batches of {n} claims, median; CPU oracle of spec/ALLOCATION.md "
@@ -349,7 +349,7 @@ def run_ours(args):
             cpu = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u16/u32 integer", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": dict(config(world), **({"collective": collective} if collective else {})),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_claim,
                         "d2h_bytes_per_step": 8 * n_out * world, "timer": "host wall clock around the C-ABI call",

@@ -23,9 +23,6 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 dev = torch.device("cuda", local)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
-uid = [pkg.api.Context.comm_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(uid, src=0)
-
 fails = 0
 for name, w, ctx_flags, use_peer in [
         ("fused+peer, mixed with counts/groups/invalid", pkg.synth.mixed(9000, 97, 21), 0, True),
@@ -38,6 +35,8 @@ for name, w, ctx_flags, use_peer in [
     n_per = max(b.n_out for b in lbs); n_per += n_per & 1
     ctx = pkg.api.Context(device=local, stream=stream.cuda_stream, flags=ctx_flags)
     ctx.set_table(w.table); ctx.set_inventory(lb.gpus, lb.node_off)
+    uid = [pkg.api.Context.comm_unique_id() if rank == 0 else None]      # one NCCL unique id per communicator
+    dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(uid[0], rank, world)
     if use_peer:
         hs = [None] * world
