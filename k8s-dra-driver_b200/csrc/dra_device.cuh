@@ -781,6 +781,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t lop3_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0xFE;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t lop3_nor(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
 __device__ __forceinline__ void sts32_if(bool p, uint32_t addr, uint32_t v) {     // predicated, no branch
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
 }
@@ -834,13 +840,15 @@ struct NodeCtx {
     Lane L; Dead D; OutSink sink;
     uint32_t lane, ltmask, g0, m0, k_next;
     uint32_t gate;                 // 0xFFFF on lanes whose GPU can take MIG devices at all, else 0
+    bool small8;                   // homogeneous node whose table row has no shape larger than 8 slices
+    bool offer_any;                // some GPU of the node is MIG-enabled and available (offers its table row)
     uint32_t live_addr;            // shared: 32 prepared records x 32 B, followed by 32 result words
     uint32_t tbl_addr;             // shared: placement table (u32 cells)
     const uint32_t* tbl_ptr;       // same table for the generic step
     bool homog, mig_ok, mig_offer, have_off;
     SelCtx sc;
     bool prof_on = false;          // instrumentation: cycle accumulators of the three parts of segment_run
-    long long t_pre = 0, t_loop = 0, t_epi = 0; uint32_t n_live = 0;
+    long long t_pre = 0, t_loop = 0, t_epi = 0, t_pre_a = 0, t_fetch = 0; uint32_t n_live = 0;
 
     __device__ __forceinline__ void begin(uint4 rec, bool valid) {
         constexpr uint32_t BLOCKED = DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE;
@@ -853,6 +861,9 @@ struct NodeCtx {
         gate = mig_ok ? 0xFFFFu : 0u;
         m0 = __shfl_sync(FULLMASK, L.model, 0);
         homog = __all_sync(FULLMASK, !L.valid || L.model == m0);     // one placement-table row for the node
+        offer_any = __any_sync(FULLMASK, mig_offer);
+        small8 = homog && __all_sync(FULLMASK, lane >= DRA_MAX_PROFILES ||
+                                     (lds32(tbl_addr + ((m0 * DRA_MAX_PROFILES + (lane & (DRA_MAX_PROFILES - 1))) << 2)) & 0xFFu) <= 8u);
     }
 };
 
@@ -870,30 +881,32 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     long long tq0 = 0; if (x.prof_on) tq0 = clock64();
     const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
     const uint32_t dst = c.y, mem = c.z, group = c.w;
+    // Straight-line and predicated: nested divergent regions cost this warp more than the arithmetic they skip
+    // (r01f timeline: 760 -> see profiles/).  The rare paths (range error, multi-slot emission) sit behind votes.
     bool live = present && pos >= x.k_next;
     const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : prof;
     const uint32_t sel = claim_sel(kind, mem, group);
-    if (live && claim_invalid(kind, prof, count, x.have_off)) {            // spec §3 (unknown selector ids: generic step)
-        if (dst < sink.n_out) sink.put(dst, DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
-        else sink.err.set(ERR_OUT_RANGE);
-        live = false;
-    }
-    const uint32_t slots = kind == DRA_KIND_GPU ? count : 1u;
+    const bool inval = claim_invalid(kind, prof, count, x.have_off);       // spec §3 (unknown selector ids: generic step)
+    const uint32_t slots = (kind == DRA_KIND_GPU && !inval) ? count : 1u;
     // co-location runs and claims with a selector take the generic step (own range checks, no failure memo)
-    const bool is_group = (kind == DRA_KIND_MIG && group != 0) || sel != 0;
-    if (live && !is_group && (dst > sink.n_out || slots > sink.n_out - dst)) { sink.err.set(ERR_OUT_RANGE); live = false; }
-    if (live && !is_group) {                                               // shapes that already failed here
-        bool dead = false; uint32_t st = DRA_ST_NO_CAPACITY;
-        if (kind == DRA_KIND_MIG) {
-            const uint32_t pbit = 1u << prof;
-            if (D.bad & pbit) { dead = true; st = DRA_ST_BAD_PROFILE; } else if (D.nocap & pbit) dead = true;
-        } else if (kind == DRA_KIND_GPU) dead = count >= D.gpu_min;
-        else { dead = (uint64_t)mem >= D.sh_min; st = DRA_ST_MEM_LIMIT; }
-        if (dead) {
-            for (uint32_t s_ = 0; s_ < slots; ++s_) sink.put(dst + s_, DRA_GPU_NONE, meta(0, 0, op, st));
-            live = false;
-        }
+    const bool is_group = !inval && ((kind == DRA_KIND_MIG && group != 0) || sel != 0);
+    const bool oor = live && !is_group && (inval ? dst >= sink.n_out : (dst > sink.n_out || slots > sink.n_out - dst));
+    uint32_t st = inval ? (uint32_t)DRA_ST_INVALID : 0xFFu;                // 0xFF: nothing to emit, the claim stays live
+    {                                                                      // shapes that already failed here
+        const uint32_t pbit = 1u << (prof & 31u);
+        const bool mig = kind == DRA_KIND_MIG, gpu = kind == DRA_KIND_GPU;
+        const bool dead = mig ? ((D.bad | D.nocap) & pbit) != 0 : gpu ? count >= D.gpu_min : (uint64_t)mem >= D.sh_min;
+        const uint32_t dst_ = mig ? ((D.bad & pbit) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY) : gpu ? DRA_ST_NO_CAPACITY : DRA_ST_MEM_LIMIT;
+        st = (!inval && !is_group && dead) ? dst_ : st;
     }
+    const bool emit = live && !oor && st != 0xFFu;
+    if (emit && slots == 1u) sink.put(dst, DRA_GPU_NONE, meta(0, 0, op, st));
+    if (__any_sync(FULLMASK, oor || (emit && slots != 1u))) {              // rare
+        if (oor) sink.err.set(ERR_OUT_RANGE);
+        if (emit && slots != 1u) for (uint32_t s_ = 0; s_ < slots; ++s_) sink.put(dst + s_, DRA_GPU_NONE, meta(0, 0, op, st));
+    }
+    live = live && !oor && st == 0xFFu;
+    if (x.prof_on) x.t_pre_a += clock64() - tq0;           // validity / range / dead-shape part of the pre-pass
     // prepared record of a live claim (what the serial step needs, already unpacked):
     //   r0 = {s1, s2, s3, s4}  shift schedule (MIG) | {count or mem or position, 0, 0, 0}
     //   r1 = {smask | prof<<16 | class<<24, first out slot, OutRec meta (size<<8 | prof<<16), (1<<size)-1}
@@ -901,6 +914,7 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     if (lm == 0) return;
     if (live) {
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, dst, 0, 0);
+        uint32_t fail_word = 0;
         if (is_group) { r0.x = pos; r1.x = 4u << 24; }
         else if (kind == DRA_KIND_MIG) {
             const uint32_t e = lds32(x.tbl_addr + ((x.m0 * DRA_MAX_PROFILES + prof) << 2));   // homogeneous node: one cell for all GPUs
@@ -909,10 +923,15 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             r1.x = (e >> 16) | (prof << 16) | (1u << 24);
             r1.z = (size << 8) | (prof << 16);
             r1.w = (1u << size) - 1u;
+            // the record's result word starts out as its failure: static on a homogeneous node (the row offers the
+            // shape or it does not); the lean loop only overwrites it on success
+            fail_word = 0xFFu | (((x.offer_any && (e >> 16) != 0) ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE) << 24);
         } else if (kind == DRA_KIND_GPU) { r0.x = count; r1.x = 2u << 24; }
         else { r0.x = mem; r1.x = 3u << 24; }
-        const uint32_t at = x.live_addr + ((uint32_t)__popc(lm & x.ltmask) << 5);
+        const uint32_t qi = (uint32_t)__popc(lm & x.ltmask);
+        const uint32_t at = x.live_addr + (qi << 5);
         sts128(at, r0); sts128(at + 16, r1);
+        sts32(x.live_addr + 1024 + (qi << 2), fail_word);
     }
     __syncwarp();
     const uint32_t nlive = (uint32_t)__popc(lm);
@@ -974,7 +993,14 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             }
         } else {                                           // co-location run: generic step (emits its own records)
             const uint32_t pj = r0.x;
-            if (pj >= x.k_next) x.k_next = pj + node_step_cold(L, D, lane, g0, x.tbl_ptr, get, pj, cnt, sink, x.have_off, x.sc);
+            if (pj >= x.k_next) {
+                // by COPY: the out-of-line call takes references, and a reference into the node context would
+                // pin the whole context (lane state, memo, sink) in local memory — every access an LDL
+                Lane Lt = L; Dead Dt = D; auto St = sink;
+                const uint32_t used = node_step_cold(Lt, Dt, lane, g0, x.tbl_ptr, get, pj, cnt, St, x.have_off, x.sc);
+                L = Lt; D = Dt; sink = St;
+                x.k_next = pj + used;
+            }
         }
     };
     // Common case — every live record of the segment is a plain MIG claim on a homogeneous node: a loop with
@@ -1008,38 +1034,40 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             sstep(b0, q + 1);
         }
     } else if (fast) {
-        auto fstep = [&](const uint4 r0, const uint4 r1, const uint32_t q) {
-            const uint32_t pj = (r1.x >> 16) & 0xFFu;
-            const uint32_t deadm = D.bad | D.nocap;
-            uint32_t t = ~L.busy & x.gate;
-            t &= t >> r0.x; t &= t >> r0.y; t &= t >> r0.z; t &= t >> r0.w;
-            uint32_t cand = t & r1.x & 0xFFFFu;
-            cand = ((deadm >> pj) & 1u) ? 0u : cand;                       // a shape that died earlier: nobody bids (no branch)
+        // Lean step (profiles/chain_bench.cu: 66-72 cycles/record against 123 for the r01e form).  A single warp is
+        // bound by max(loop-carried chain at ~6 cycles per dependent ALU op, 2 cycles per ALU instruction), so:
+        //  - the state is the FREE mask (no NOT on the chain), 0 on lanes that cannot take MIG devices;
+        //  - the start mask is static: a shape that died earlier simply finds no candidate (occupancy only grows), so
+        //    the dead-shape memo is not read here; it is brought up to date once, in the epilogue;
+        //  - no failure handling at all: the pre-pass initialised every result word to the shape's (static) failure;
+        //  - winner test = one LOP3 with a predicate output, update = select between two precomputed masks.
+        uint32_t fre = ~L.busy & x.gate;
+        const uint32_t lemask = lanebit | (lanebit - 1u), gate = x.gate;
+        auto fstep = [&](auto NRtag, const uint4 r0, const uint4 r1, const uint32_t q) {
+            uint32_t t = fre;
+            t &= t >> r0.x; t &= t >> r0.y; t &= t >> r0.z;
+            if (decltype(NRtag)::value == 4) t &= t >> r0.w;               // shapes of 9..16 slices
+            const uint32_t cand = t & r1.x & gate;                         // gate has 16 bits: drops prof/class of r1.x
             const uint32_t b = __ballot_sync(FULLMASK, cand != 0);
             const uint32_t low = cand & (0u - cand);                       // lowest start, one-hot
-            const bool win = (b & (0u - b)) == lanebit;                    // lowest GPU; b == 0: nobody
-            L.busy |= win ? r1.w * low : 0u;                               // predicated: no divergent branch on the chain
-            sts32_if(win, res_addr + (q << 2), lane | (low << 8));         // start is decoded from `low` in the epilogue
-            if (b == 0) {                                                  // rare: the shape fails (now, or already dead)
-                uint32_t stt;
-                if ((deadm >> pj) & 1u) stt = ((D.bad >> pj) & 1u) ? DRA_ST_BAD_PROFILE : DRA_ST_NO_CAPACITY;
-                else {
-                    const bool any = __ballot_sync(FULLMASK, x.mig_offer && (r1.x & 0xFFFFu) != 0) != 0;
-                    if (any) D.nocap |= 1u << pj; else D.bad |= 1u << pj;
-                    stt = any ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE;
-                }
-                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | (stt << 24));
+            const uint32_t freW = fre & ~(r1.w * low);                     // off the chain: overlaps the vote
+            const bool lose = ((b & lemask) ^ lanebit) != 0;               // win: lowest GPU with a candidate
+            fre = lose ? fre : freW;
+            sts32_if(!lose, res_addr + (q << 2), lane + (cand << 8));      // start = lowest set bit, decoded in the epilogue
+        };
+        auto floop = [&](auto NRtag) {
+            uint4 a0 = lds128(x.live_addr), a1 = lds128(x.live_addr + 16), b0, b1;
+            for (uint32_t q = 0; q < nlive; q += 2) {
+                const uint32_t nb_ = x.live_addr + ((q + 1) << 5);
+                if (q + 1 < nlive) { b0 = lds128(nb_); b1 = lds128(nb_ + 16); }
+                fstep(NRtag, a0, a1, q);
+                if (q + 1 >= nlive) break;
+                if (q + 2 < nlive) { a0 = lds128(nb_ + 32); a1 = lds128(nb_ + 48); }
+                fstep(NRtag, b0, b1, q + 1);
             }
         };
-        uint4 a0 = lds128(x.live_addr), a1 = lds128(x.live_addr + 16), b0, b1;
-        for (uint32_t q = 0; q < nlive; q += 2) {
-            const uint32_t nb_ = x.live_addr + ((q + 1) << 5);
-            if (q + 1 < nlive) { b0 = lds128(nb_); b1 = lds128(nb_ + 16); }
-            fstep(a0, a1, q);
-            if (q + 1 >= nlive) break;
-            if (q + 2 < nlive) { a0 = lds128(nb_ + 32); a1 = lds128(nb_ + 48); }
-            fstep(b0, b1, q + 1);
-        }
+        if (x.small8) floop(std::integral_constant<int, 3>{}); else floop(std::integral_constant<int, 4>{});
+        L.busy = gate ? (~fre & 0xFFFFu) : L.busy;
     } else {
     // ping-pong: the next record is in flight while the current one is stepped, no register shuffling
     uint4 a0 = lds128(x.live_addr), a1 = lds128(x.live_addr + 16), b0, b1;
@@ -1055,17 +1083,29 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     __syncwarp();
     long long tq2 = 0; if (x.prof_on) { tq2 = clock64(); x.t_loop += tq2 - tq1; }
     // epilogue: lane q composes and stores the OutRec of live record q (MIG / SHARED)
-    if (lane < nlive) {
-        const uint4 r1 = lds128(x.live_addr + (lane << 5) + 16);
+    uint32_t died_nocap = 0, died_bad = 0;                 // lean loop: shapes that failed in this segment
+    {
+        // predicated straight-line code (one store), not nested branches
+        const bool have = lane < nlive;
+        uint4 r1 = make_uint4(0, 0, 0, 0); uint32_t res = 0;
+        if (have) { r1 = lds128(x.live_addr + (lane << 5) + 16); res = lds32(res_addr + (lane << 2)); }
         const uint32_t cls = r1.x >> 24;
-        if (cls == 1u || cls == 3u) {
-            const uint32_t res = lds32(res_addr + (lane << 2));
-            const uint32_t w = res & 0xFFu, st_ = res >> 24;
-            const uint32_t prof_ = cls == 1u ? ((r1.x >> 16) & 0xFFu) : (uint32_t)DRA_PROFILE_SHARED;
-            if (w == 0xFFu) sink.put(r1.y, DRA_GPU_NONE, meta(0, 0, prof_, st_));
-            else if (fast) sink.put(r1.y, g0 + w, r1.z | ((uint32_t)__ffs((res >> 8) & 0xFFFFu) - 1u));
-            else sink.put(r1.y, g0 + w, meta((res >> 8) & 0xFFu, (res >> 16) & 0xFFu, prof_, DRA_ST_OK));
-        }
+        const bool mine = have && (cls == 1u || cls == 3u);
+        const uint32_t w = res & 0xFFu, st_ = res >> 24;
+        const uint32_t prof_ = cls == 1u ? ((r1.x >> 16) & 0xFFu) : (uint32_t)DRA_PROFILE_SHARED;
+        const bool failed = w == 0xFFu;
+        const uint32_t pbit = 1u << (prof_ & 31u);
+        died_nocap = (fast && mine && failed && st_ == DRA_ST_NO_CAPACITY) ? pbit : 0u;
+        died_bad = (fast && mine && failed && st_ != DRA_ST_NO_CAPACITY) ? pbit : 0u;
+        const uint32_t m_ok = fast ? (r1.z | ((uint32_t)__ffs((res >> 8) & 0xFFFFu) - 1u))
+                                   : meta((res >> 8) & 0xFFu, (res >> 16) & 0xFFu, prof_, DRA_ST_OK);
+        const uint32_t gpu_ = failed ? (uint32_t)DRA_GPU_NONE : g0 + w;
+        const uint32_t m_ = failed ? meta(0, 0, prof_, st_) : m_ok;
+        if (mine) sink.put(r1.y, gpu_, m_);
+    }
+    if (fast) {                                            // the dead-shape memo, for the next segment's pre-pass
+        D.nocap |= __reduce_or_sync(FULLMASK, died_nocap);
+        D.bad |= __reduce_or_sync(FULLMASK, died_bad);
     }
     if (x.prof_on) x.t_epi += clock64() - tq2;
     __syncwarp();
@@ -1385,14 +1425,17 @@ k_fused(const PackArgs a) {
             const uint32_t nseg = (cnt + SEG - 1) / SEG;
             for (uint32_t seg = 0; seg < nseg; ++seg) {
                 uint4 c_nxt = make_uint4(0xFFu, 0, 0, 0); bool p_nxt = false;
+                const long long tf0 = x.prof_on ? clock64() : 0;
                 if (seg + 1 < nseg) fetch(seg + 1, c_nxt, p_nxt);       // in flight while this segment is packed
+                if (x.prof_on) x.t_fetch += clock64() - tf0;
                 segment_run(x, c_cur, p_cur, seg * SEG + lane, get, cnt);
                 c_cur = c_nxt; p_cur = p_nxt;
             }
             if (lane < ng) a.inv_dst[g0 + lane] = x.L.store(rec);
             DRA_STAMP(6);
             if (a.timeline && lane == 0) {
-                a.timeline[blockIdx.x * 8 + 7] = cnt | ((unsigned long long)x.n_live << 32);
+                a.timeline[blockIdx.x * 8 + 7] = (cnt & 0xFFFFu) | ((unsigned long long)(x.n_live & 0xFFFFu) << 16) |
+                    ((unsigned long long)(x.t_fetch & 0xFFFF) << 32) | ((unsigned long long)(x.t_pre_a & 0xFFFF) << 48);
                 a.timeline[blockIdx.x * 8 + 0] = (unsigned long long)x.t_pre | ((unsigned long long)x.t_loop << 20) | ((unsigned long long)x.t_epi << 40);
             }
         }

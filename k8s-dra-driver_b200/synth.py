@@ -250,3 +250,38 @@ def with_selectors(w: Workload, seed: int = 1, frac: int = 3):
 
 
 CONFIGS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}
+
+
+def homog(n_claim: int = 3000, n_node: int = 24, seed: int = 1, model: int = 0, wide16: bool = False,
+          max_width: int = 32) -> Workload:
+    """Homogeneous all-MIG nodes of widths 1..max_width with pre-occupied, fully-allocated and unavailable
+    GPUs, MIG-only claims incl. unsupported profiles: the workload class of the packers' fast loops (the
+    64-bit SWAR form for <= 8 GPUs x <= 8 slices, the ballot form for anything wider).  ``wide16`` swaps in a
+    synthetic 16-slice part so that occupancy masks do not fit a byte."""
+    r = splitmix64(BASE_SEED + 900 + seed, 8 * (n_node * 40 + n_claim) + 64)
+    sizes = 1 + (r[:n_node] % np.uint64(max_width)).astype(np.int64)
+    sizes[::3] = np.minimum(sizes[::3], 8)
+    g, off = R.make_inventory(list(sizes), mig=True, model=model)
+    ng = len(g)
+    a = r[n_node: n_node + 3 * ng]
+    t = R.default_table()
+    if wide16:
+        t[model] = 0
+        t[model, R.GI_1_SLICE] = (1, 0, 0xFFFF)
+        t[model, R.GI_2_SLICE] = (2, 0, 0x5555)
+        t[model, R.GI_3_SLICE] = (5, 0, R.mask_of((0, 5, 10)))
+        t[model, R.GI_4_SLICE] = (8, 0, R.mask_of((0, 8)))
+        t[model, R.GI_7_SLICE] = (16, 0, 1)
+    width = 0xFFFF if wide16 else (0xFF if model == 0 else 0xF)
+    pre = (a[0:ng] % np.uint64(65536)).astype(np.uint16) & np.uint16(width)
+    g["busy"] = np.where(a[0:ng] % np.uint64(4) == 0, pre, 0)
+    g["flags"] |= np.where(a[ng:2 * ng] % np.uint64(13) == 0, R.GPU_UNAVAILABLE, 0).astype(np.uint8)
+    g["flags"] |= np.where(a[2 * ng:3 * ng] % np.uint64(11) == 0, R.GPU_FULL_ALLOCATED, 0).astype(np.uint8)
+    b = r[n_node + 3 * ng: n_node + 3 * ng + 2 * n_claim]
+    c = np.zeros(n_claim, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_MIG
+    c["count"] = 1
+    profs = np.array([0, 0, 0, 0, 1, 1, 2, 3, 4, 7, 9, 5, 12], dtype=np.uint8)
+    c["profile"] = profs[(b[0::2] % np.uint64(len(profs))).astype(np.int64)]
+    c["node"] = (b[1::2] % np.uint64(n_node)).astype(np.uint32)
+    return Workload(f"homog{seed}", g, off, t, c).finish()

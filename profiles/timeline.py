@@ -23,9 +23,11 @@ for k, nm in enumerate(names):
     d = (node[:, k + 2] - node[:, k + 1]).astype(np.int64)
     print(f"{nm:36s} cycles: median {int(np.median(d)):6d}  p90 {int(np.percentile(d, 90)):6d}  max {int(d.max()):6d}")
 tot = (node[:, 6] - node[:, 1]).astype(np.int64)
-cnt = (node[:, 7] & np.uint64(0xFFFFFFFF)).astype(np.int64); nlive = (node[:, 7] >> np.uint64(32)).astype(np.int64)
+cnt = (node[:, 7] & np.uint64(0xFFFF)).astype(np.int64); nlive = ((node[:, 7] >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.int64)
+fetch = ((node[:, 7] >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.int64); pre_a = (node[:, 7] >> np.uint64(48)).astype(np.int64)
 pre = (node[:, 0] & np.uint64(0xFFFFF)).astype(np.int64); loop = ((node[:, 0] >> np.uint64(20)) & np.uint64(0xFFFFF)).astype(np.int64); epi = (node[:, 0] >> np.uint64(40)).astype(np.int64)
 print("total in-CTA cycles: median %d  max %d" % (np.median(tot), tot.max()))
 print("claims/node median %d max %d; live records/node median %d max %d" % (np.median(cnt), cnt.max(), np.median(nlive), nlive.max()))
 print("inside pack: pre-pass median %d  serial loop median %d (%.0f cycles/live record)  epilogue median %d" % (np.median(pre), np.median(loop), np.median(loop / np.maximum(nlive, 1)), np.median(epi)))
+print("  pre-pass part a (validity/range/dead-shape emission) median %d; next-segment fetch median %d; pack minus (pre+loop+epi+fetch) median %d" % (np.median(pre_a), np.median(fetch), np.median((node[:, 6] - node[:, 5]).astype(np.int64) - pre - loop - epi - fetch)))
 i = int(np.argmax(tot)); print("slowest CTA", i, "pack", int(node[i, 6] - node[i, 5]), "pre/loop/epi", int(pre[i]), int(loop[i]), int(epi[i]), "claims", int(cnt[i]), "live", int(nlive[i]))

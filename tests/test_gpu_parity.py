@@ -74,6 +74,19 @@ def test_cuda_matches_oracle_fuzz(pkg, ctx, oracle, seed):
     _assert_same(out, inv, ref_out, ref_inv, f"mixed seed {seed}")
 
 
+# ---- the packers' fast loops: 64-bit SWAR node state (<= 8 GPUs x <= 8 slices) and the ballot form (wider) ----
+@pytest.mark.parametrize("seed,model,wide16,max_width", [
+    (0, 0, False, 8), (1, 0, False, 32), (2, 1, False, 8), (3, 0, True, 8), (4, 0, True, 32), (5, 1, False, 32),
+    (6, 0, False, 1), (7, 0, False, 9)])
+def test_fast_loops_match_oracle(pkg, ctx, oracle, seed, model, wide16, max_width):
+    for n_claim, n_node in ((700, 5), (6000, 40), (30000, 300)):
+        w = pkg.synth.homog(n_claim, n_node, seed, model=model, wide16=wide16, max_width=max_width)
+        out, inv = _run(ctx, w)
+        ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims)
+        _assert_same(out, inv, ref_out, ref_inv, f"homog seed {seed} {n_claim}x{n_node}")
+        assert (out["status"] == 0).any() and (out["status"] != 0).any()
+
+
 def test_edge_cases(pkg, ctx, oracle):
     R = pkg.records
     t = R.default_table()

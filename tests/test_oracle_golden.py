@@ -119,6 +119,20 @@ def test_oracle_matches_naive_restatement(pkg, oracle, seed):
                (b["busy"], b["flags"], b["mem_free_mib"], b["share_cnt"])
 
 
+@pytest.mark.parametrize("seed,model,wide16,max_width", [(0, 0, False, 8), (3, 0, True, 8), (4, 0, True, 32),
+                                                        (2, 1, False, 8), (7, 0, False, 9)])
+def test_oracle_matches_naive_on_homogeneous_nodes(pkg, oracle, seed, model, wide16, max_width):
+    """The workload class of the CUDA packers' fast loops, incl. a 16-slice part."""
+    from oracle import naive
+    w = pkg.synth.homog(900, 6, seed, model=model, wide16=wide16, max_width=max_width)
+    out, after = oracle.allocate(w.gpus, w.node_off, w.table, w.claims)
+    tbl = [[(int(w.table[m, p]["size"]), int(w.table[m, p]["start_mask"])) for p in range(16)] for m in range(16)]
+    nout, nafter = naive.allocate(_dicts(w.gpus), [int(x) for x in w.node_off], tbl, _dicts(w.claims))
+    assert [tuple(int(v) for v in r) for r in out] == nout
+    assert [int(a["busy"]) for a in after] == [b["busy"] for b in nafter]
+    assert (out["status"] == 0).any() and (out["status"] != 0).any()
+
+
 def test_oracle_mt_equals_single_thread(pkg, oracle):
     w = pkg.synth.cfg2(5000, 60)
     a, ga = oracle.allocate(w.gpus, w.node_off, w.table, w.claims)
