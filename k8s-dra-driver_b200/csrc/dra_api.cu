@@ -107,7 +107,7 @@ struct dra_ctx {
     float timings[5] = {0, 0, 0, 0, 0};
     uint32_t ev_mask = 0;
     int hist8_smem_set = 0, hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0, fused_smem_set_stage = 0, fused_smem_set_cl = 0;
-    uint64_t fused_max_work = 6000000ull;   // n_node * n_claim up to which the single-launch kernel is used
+    uint64_t fused_max_work = 3000000ull;   // n_node * n_claim up to which the single-launch kernel is used
 
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -225,6 +225,18 @@ int upload_table(dra_ctx* ctx) {
     return DRA_OK;
 }
 
+// Kernel launch with (optionally) the programmatic-dependent-launch attribute: the kernel's CTAs may be scheduled
+// while its predecessor in the stream drains; it blocks in griddepcontrol.wait until that grid has completed.
+template <typename... KA, typename... A>
+static cudaError_t launch_k(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, A&&... args) {
+    cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&lc, k, static_cast<KA>(args)...);
+}
+
 struct Prof {          // event i brackets stage i: [hist, scan, scatter, pack/fused, all-gather]
     dra_ctx* c; int i = 0;
     explicit Prof(dra_ctx* ctx) : c(ctx) { c->ev_mask = 0; rec(0); }
@@ -259,7 +271,10 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     static const bool no_stage = getenv("DRA_NO_STAGE") != nullptr;          // experiment switch
     const bool stage = !no_stage && n_claim <= FUSED_NW * FU_PIECE * FU_MAXPIECE && fused_smem_bytes(n_claim, FUSED_NW, true) <= 225 * 1024;
     const size_t fused_smem = fused_smem_bytes(n_claim, FUSED_NW, stage);
-    const bool fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) &&
+    // Measured crossover against the sort path (profiles/path_crossover_r01f.txt): the single launch costs about
+    // 4 us + 1.2 us per 1000 claims while all CTAs fit one wave, the sort path 23 us + 0.25 us per 1000 claims.
+    const uint32_t fused_max_claims = n_node + 1 <= 148 ? 20000u : 12000u;
+    const bool fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) && n_claim <= fused_max_claims &&
                        (uint64_t)n_node * n_claim <= ctx->fused_max_work && fused_smem <= 225 * 1024 && n_node <= 16384;
     if (fused) {
         if (tail) { a.peer = *tail; if (tail_done) *tail_done = true; }
@@ -307,6 +322,10 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         return DRA_OK;
     }
 
+    // sort path: the kernels after the first are programmatic dependents of their predecessor (launch latency and
+    // prologue overlap the predecessor's tail); not while per-kernel events are being recorded
+    static const bool no_pdl = getenv("DRA_NO_PDL") != nullptr;
+    const bool pdl = !no_pdl && !ctx->profiling;
     if (flags & DRA_F_NODE_SORTED) {
         uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
         k_sorted_prep<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
@@ -342,7 +361,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
                 if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
                 k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank);
                 prof.mark();
-                k_bucket_scan8<<<(n_node + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8);
+                CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 255) / 256), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
                 prof.mark();
             } else {
                 size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
@@ -353,12 +372,12 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
                 }
                 k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
                 prof.mark();
-                k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off);
+                CU(launch_k(k_bucket_scan, dim3(1), dim3(1024), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off));
                 prof.mark();
             }
             uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
-            k_bucket_scatter<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
-                                                              ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err);
+            CU(launch_k(k_bucket_scatter, dim3(blocks), dim3(256), 0, ctx->stream, pdl, d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
+                        ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err));
             prof.mark();
             ctx->launches += 3;
         }
@@ -367,8 +386,8 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     a.sorted = ctx->d_sorted;
     a.claim_off = ctx->d_claim_off;
     if (n_node) {
-        if (n_node <= 148u * 16u) k_pack<1><<<n_node, 32, pack_smem_bytes(1), ctx->stream>>>(a);
-        else k_pack<4><<<std::min((n_node + 3) / 4, 148u * 8u), 128, pack_smem_bytes(4), ctx->stream>>>(a);
+        if (n_node <= 148u * 16u) CU(launch_k(k_pack<1>, dim3(n_node), dim3(32), pack_smem_bytes(1), ctx->stream, pdl, a));
+        else CU(launch_k(k_pack<4>, dim3(std::min((n_node + 3) / 4, 148u * 8u)), dim3(128), pack_smem_bytes(4), ctx->stream, pdl, a));
         ctx->launches += 1;
     }
     prof.mark();

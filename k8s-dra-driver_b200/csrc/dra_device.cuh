@@ -45,6 +45,12 @@ struct Err {
 //                    z = mem_limit_mib ; w = group
 // OutRec   as uint2: x = gpu ; y = start | size<<8 | profile<<16 | status<<24
 
+// Programmatic dependent launch (sort path: hist -> scan -> scatter -> pack).  A producer lets the next kernel's
+// CTAs be scheduled early; a consumer blocks until the producer grid has completed and its writes are visible.
+// Both are no-ops for a launch without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -384,6 +390,7 @@ __global__ void __launch_bounds__(32)
 k_bucket_hist(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node, uint32_t T,
               uint32_t* __restrict__ hist, uint16_t* __restrict__ rank) {
     extern __shared__ uint16_t cnt[];
+    pdl_trigger();
     const uint32_t lane = threadIdx.x, nb = n_node + 1;
     const uint32_t nbits = 32u - (uint32_t)__clz(n_node);          // keys are 0..n_node
     for (uint32_t n = lane; n < nb; n += 32) cnt[n] = 0;
@@ -415,6 +422,7 @@ k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node,
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry_s, total_s;
     const uint32_t nb = n_node + 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_trigger(); pdl_wait();
     if (tid == 0) carry_s = 0;
     __syncthreads();
     for (uint32_t n0 = 0; n0 < nb; n0 += 1024) {
@@ -463,6 +471,7 @@ __global__ void __launch_bounds__(256)
 k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
                uint32_t* __restrict__ hist, uint16_t* __restrict__ rank) {
     extern __shared__ uint16_t cnt8[];                              // [8][nbp]
+    pdl_trigger();
     const uint32_t nb = n_node + 1, nbp = (nb + 1) & ~1u;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nbits = 32u - (uint32_t)__clz(n_node);
@@ -511,6 +520,7 @@ __global__ void __launch_bounds__(256)
 k_bucket_scan8(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node, uint32_t* __restrict__ claim_off,
                uint32_t* __restrict__ ticket) {
     const uint32_t nb = n_node + 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_trigger(); pdl_wait();
     const uint32_t n = blockIdx.x * 256 + tid;
     if (n < nb) {
         uint32_t run = 0, t = 0;
@@ -570,6 +580,7 @@ k_bucket_scatter(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_
     if (i >= n_claim) return;
     uint4 c = __ldg(&claims[i]);
     const uint32_t dst = out_off ? __ldg(&out_off[i]) : i;
+    pdl_trigger(); pdl_wait();                             // the inputs above do not come from the chain
     const uint32_t nb = n_node + 1;
     if (c.y >= n_node) {
         const uint32_t kind = c.x & 0xFFu;
@@ -600,6 +611,7 @@ k_bucket_small(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_no
                const uint32_t* __restrict__ out_off, uint32_t* __restrict__ claim_off,
                uint4* __restrict__ sorted, uint2* __restrict__ out, uint32_t n_out, Err err, Prefetch pf) {
     extern __shared__ uint32_t sm_u32[];
+    pdl_trigger();
     const uint32_t nb = n_node + 1, nbp = (nb + 1) & ~1u;
     uint32_t* off = sm_u32;                                        // [nbp]
     uint16_t* cnt = reinterpret_cast<uint16_t*>(off + nbp);        // [32][nbp]
@@ -720,6 +732,7 @@ __global__ void __launch_bounds__(256)
 k_sorted_prep(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
               const uint32_t* __restrict__ out_off, uint32_t* __restrict__ claim_off,
               uint4* __restrict__ sorted, uint2* __restrict__ out, uint32_t n_out, Err err) {
+    pdl_trigger();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && n_claim == 0) { for (uint32_t n = 0; n <= n_node + 1; ++n) claim_off[n] = 0; }
     if (i >= n_claim) return;
@@ -927,7 +940,7 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
             // shape or it does not); the lean loop only overwrites it on success
             fail_word = 0xFFu | (((x.offer_any && (e >> 16) != 0) ? DRA_ST_NO_CAPACITY : DRA_ST_BAD_PROFILE) << 24);
         } else if (kind == DRA_KIND_GPU) { r0.x = count; r1.x = 2u << 24; }
-        else { r0.x = mem; r1.x = 3u << 24; }
+        else { r0.x = mem; r1.x = 3u << 24; fail_word = 0xFFu | (DRA_ST_MEM_LIMIT << 24); }
         const uint32_t qi = (uint32_t)__popc(lm & x.ltmask);
         const uint32_t at = x.live_addr + (qi << 5);
         sts128(at, r0); sts128(at + 16, r1);
@@ -1012,17 +1025,16 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
     if (fast_sh) {
         // every live record is a SHARED claim (spec §7): flags cannot change inside the segment
         const bool share_ok = L.valid && !(L.flags & BLOCKED);
+        // lean, like the MIG loop below: the memo is not read (a limit at or above one that failed finds no GPU:
+        // free memory only shrinks), failures are the pre-initialised result words, memo update in the epilogue
+        const uint32_t lemask = lanebit | (lanebit - 1u);
         auto sstep = [&](const uint4 r0, const uint32_t q) {
             const uint32_t mj = r0.x;
-            const bool elig = share_ok && L.share < 0xFFFFu && L.mem >= mj && (uint64_t)mj < D.sh_min;
+            const bool elig = share_ok && L.share < 0xFFFFu && L.mem >= mj;
             const uint32_t b = __ballot_sync(FULLMASK, elig);
-            const bool win = (b & (0u - b)) == lanebit;                    // lowest GPU; b == 0: nobody
-            L.mem -= win ? mj : 0u; L.share += win ? 1u : 0u;
-            sts32_if(win, res_addr + (q << 2), lane);
-            if (b == 0) {
-                if ((uint64_t)mj < D.sh_min) D.sh_min = mj;
-                sts32_if(lane == 0, res_addr + (q << 2), 0xFFu | (DRA_ST_MEM_LIMIT << 24));
-            }
+            const bool lose = ((b & lemask) ^ lanebit) != 0;               // win: lowest eligible GPU
+            L.mem = lose ? L.mem : L.mem - mj; L.share += lose ? 0u : 1u;
+            sts32_if(!lose, res_addr + (q << 2), lane);
         };
         uint4 a0 = lds128(x.live_addr), b0;
         for (uint32_t q = 0; q < nlive; q += 2) {
@@ -1102,6 +1114,11 @@ __device__ __forceinline__ void segment_run(NodeCtx& x, const uint4 c, const boo
         const uint32_t gpu_ = failed ? (uint32_t)DRA_GPU_NONE : g0 + w;
         const uint32_t m_ = failed ? meta(0, 0, prof_, st_) : m_ok;
         if (mine) sink.put(r1.y, gpu_, m_);
+        if (fast_sh) {                                     // smallest limit that failed in this segment
+            const uint32_t fm = (mine && failed) ? lds32(x.live_addr + (lane << 5)) : 0xFFFFFFFFu;
+            const uint32_t mn = __reduce_min_sync(FULLMASK, fm);
+            if ((uint64_t)mn < D.sh_min && mn != 0xFFFFFFFFu) D.sh_min = mn;
+        }
     }
     if (fast) {                                            // the dead-shape memo, for the next segment's pre-pass
         D.nocap |= __reduce_or_sync(FULLMASK, died_nocap);
@@ -1145,6 +1162,7 @@ k_pack(const PackArgs a) {
     }
     __syncthreads();
     if (threadIdx.x == 0) tma_load_a(sbase + PK_TBL, a.tbl, 1024u, tbar_addr);   // placement table, waited on later
+    pdl_wait();                                    // sorted claims / claim_off come from the bucketing kernels
     bool tbl_ready = false;
 
     NodeCtx x;
