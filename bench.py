@@ -197,7 +197,7 @@ def run_ours(args):
     n_claim, n_out = w.n_claim, w.n_out
     # DRA_CFG_USE_GRAPH only concerns the host-buffer call (the e2e leg): H2D -> kernel -> D2H as one graph launch
     ctx = pkg.api.Context(device=local, stream=stream.cuda_stream, max_claims=n_claim,
-                          flags=0 if args.no_graph else pkg.api.CFG_USE_GRAPH)
+                          flags=(0 if args.no_graph else pkg.api.CFG_USE_GRAPH) | (pkg.api.CFG_NO_DIRECT if args.no_direct else 0))
     ctx.set_table(w.table)
     ctx.set_inventory(w.gpus, w.node_off)
     collective = None
@@ -353,7 +353,9 @@ def run_ours(args):
                 "config": dict(config(world), **({"collective": collective} if collective else {})),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_claim,
                         "d2h_bytes_per_step": 8 * n_out * world, "timer": "host wall clock around the C-ABI call",
-                        "cuda_graph": bool(world == 1 and not args.no_graph)},
+                        "cuda_graph": bool(world == 1 and not args.no_graph and args.no_direct),
+                        "host_io": ("direct: one cooperative launch, the kernel reads the claims from / writes the OutRecs to the pinned host buffers"
+                                    if world == 1 and not args.no_direct else "copy engine: H2D, kernels, D2H")},
                 "gpu_launches": launches,
                 "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "kernel": {"fused": "k_fused", "pack": "k_pack", "bucket_hist": "k_bucket_hist",
@@ -381,6 +383,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-direct", action="store_true", help="e2e leg: copy-engine transfers around the kernel instead of direct host I/O")
     ap.add_argument("--no-graph", action="store_true", help="e2e leg: enqueue H2D / kernel / D2H separately instead of one CUDA graph")
     ap.add_argument("--nccl", action="store_true", help="N>1: use ncclAllGather instead of the peer-store all-gather")
     args = ap.parse_args()

@@ -161,6 +161,9 @@ typedef struct dra_cfg {
 #define DRA_CFG_USE_GRAPH  0x1u  /* dra_allocate_batch: replay H2D -> kernels -> D2H as ONE CUDA graph launch when a
                                     call repeats the previous call's buffers and sizes (captured on the 2nd such call) */
 #define DRA_CFG_NO_FUSED   0x2u  /* never take the single-launch path (always bucket + pack); for tests */
+#define DRA_CFG_NO_DIRECT  0x4u  /* dra_allocate_batch: never let the single-launch kernel read the claims from / write the
+                                    results to the pinned host buffers itself (direct host I/O, one cooperative launch);
+                                    always use copy-engine transfers around the kernels */
 
 /* error codes (negative) */
 #define DRA_OK        0

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libdra_alloc.so")
 
 OK, E_INVAL, E_CUDA, E_NCCL, E_NOMEM, E_STATE = 0, -1, -2, -3, -4, -5
-CFG_USE_GRAPH, CFG_NO_FUSED = 0x1, 0x2
+CFG_USE_GRAPH, CFG_NO_FUSED, CFG_NO_DIRECT = 0x1, 0x2, 0x4
 F_NODE_SORTED, F_FRESH_INVENTORY = 0x1, 0x2
 
 

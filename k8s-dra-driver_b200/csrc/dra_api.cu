@@ -108,6 +108,12 @@ struct dra_ctx {
     uint32_t ev_mask = 0;
     int hist8_smem_set = 0, hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0, fused_smem_set_stage = 0, fused_smem_set_cl = 0;
     uint64_t fused_max_work = 3000000ull;   // n_node * n_claim up to which the single-launch kernel is used
+    // direct host I/O of the single-launch kernel (DirectIO in dra_device.cuh)
+    DirectIO dio_pending{};                 // set by dra_allocate_batch for the next launch_allocate, then cleared
+    uint32_t* d_gbar = nullptr;             // grid barrier words
+    int n_sm = 0, coop_ok = 0;
+    int dio_cap_smem = -1, dio_cap_cta = 0; // co-resident CTA capacity of k_fused at dio_cap_smem bytes of shared memory
+    const void* dio_seen[3] = {nullptr, nullptr, nullptr};   // host pointers already checked to be device-visible as-is
 
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -246,6 +252,24 @@ struct Prof {          // event i brackets stage i: [hist, scan, scatter, pack/f
 };
 
 // The kernel chain of one Allocate batch on device-resident inputs.  Enqueues only.
+constexpr int FUSED_NW = 8;
+// Which kernel chain an Allocate batch takes.  Small batches: ONE launch — every node's CTA filters the claim
+// stream for itself (n_node * n_claim key tests spread over n_node SMs, data from L2) and packs; no sort, no copy.
+struct FusedPlan { bool fused, stage; size_t smem; };
+FusedPlan fused_plan(const dra_ctx* ctx, uint32_t n_claim, uint32_t flags) {
+    static const bool no_stage = getenv("DRA_NO_STAGE") != nullptr;          // experiment switch
+    const uint32_t n_node = ctx->n_node;
+    FusedPlan p;
+    p.stage = !no_stage && n_claim <= FUSED_NW * FU_PIECE * FU_MAXPIECE && fused_smem_bytes(n_claim, FUSED_NW, true) <= 225 * 1024;
+    p.smem = fused_smem_bytes(n_claim, FUSED_NW, p.stage);
+    // Measured crossover against the sort path (profiles/path_crossover_r01f.txt): the single launch costs about
+    // 4 us + 1.2 us per 1000 claims while all CTAs fit one wave, the sort path 23 us + 0.25 us per 1000 claims.
+    const uint32_t fused_max_claims = n_node + 1 <= 148 ? 20000u : 12000u;
+    p.fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) && n_claim <= fused_max_claims &&
+              (uint64_t)n_node * n_claim <= ctx->fused_max_work && p.smem <= 225 * 1024 && n_node <= 16384;
+    return p;
+}
+
 int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                     uint2* d_out, uint32_t n_out, uint32_t flags, const PeerTail* tail = nullptr, bool* tail_done = nullptr) {
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
@@ -265,17 +289,11 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     a.err = err;
     a.sel = sel_of(ctx);
 
-    // Small batches: ONE launch.  Every node's CTA filters the claim stream for itself (n_node * n_claim key
-    // tests spread over n_node SMs, data from L2) and packs — no sort, no sorted copy.
-    constexpr int FUSED_NW = 8;
-    static const bool no_stage = getenv("DRA_NO_STAGE") != nullptr;          // experiment switch
-    const bool stage = !no_stage && n_claim <= FUSED_NW * FU_PIECE * FU_MAXPIECE && fused_smem_bytes(n_claim, FUSED_NW, true) <= 225 * 1024;
-    const size_t fused_smem = fused_smem_bytes(n_claim, FUSED_NW, stage);
-    // Measured crossover against the sort path (profiles/path_crossover_r01f.txt): the single launch costs about
-    // 4 us + 1.2 us per 1000 claims while all CTAs fit one wave, the sort path 23 us + 0.25 us per 1000 claims.
-    const uint32_t fused_max_claims = n_node + 1 <= 148 ? 20000u : 12000u;
-    const bool fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) && n_claim <= fused_max_claims &&
-                       (uint64_t)n_node * n_claim <= ctx->fused_max_work && fused_smem <= 225 * 1024 && n_node <= 16384;
+    const FusedPlan plan = fused_plan(ctx, n_claim, flags);
+    const bool fused = plan.fused, stage = plan.stage;
+    const size_t fused_smem = plan.smem;
+    const DirectIO dio = ctx->dio_pending;
+    ctx->dio_pending = DirectIO{};
     if (fused) {
         if (tail) { a.peer = *tail; if (tail_done) *tail_done = true; }
         // clusters of 8 CTAs + TMA multicast when the array is staged and there are enough nodes to share it
@@ -300,7 +318,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
                 CU(cudaMalloc((void**)&ctx->d_timeline, ctx->tl_cap * 8));
             }
             CU(cudaMemsetAsync(ctx->d_timeline, 0, ctx->tl_cap * 8, ctx->stream));
-            a.timeline = ctx->d_timeline; ctx->tl_n = (n_node + 1) * 8;
+            a.timeline = ctx->d_timeline; ctx->tl_n = (n_node + 3) * 8;
         }
         prof.skip_to(3);
         // grid = one CTA per node + one CTA for the claims that name no node (+ padding to whole clusters)
@@ -312,6 +330,16 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             lc.attrs = at; lc.numAttrs = 1;
             CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, true, CLS>, a));
+        }
+        else if (stage && dio.h_claims) {
+            // direct host I/O: two grid barriers inside, so every CTA must be resident — cooperative launch
+            a.dio = dio;
+            cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
+            lc.gridDim = dim3(n_node + 1); lc.blockDim = dim3(FUSED_NW * 32); lc.dynamicSmemBytes = fused_smem; lc.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, true, 1>, a));
         }
         else if (stage) k_fused<FUSED_NW, true, 1><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
         else k_fused<FUSED_NW, false, 1><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
@@ -443,6 +471,8 @@ int dra_ctx_create(const dra_cfg* cfg, dra_ctx** out) {
     dra_ctx* c = new dra_ctx();
     c->device = cfg->device;
     c->cfg_flags = cfg->flags;
+    c->n_sm = prop.multiProcessorCount;
+    c->coop_ok = prop.cooperativeLaunch && prop.unifiedAddressing && prop.canUseHostPointerForRegisteredMem;
     ctx = c;
     auto bail = [&](int rc) { g_create_err = c->err; dra_ctx_destroy(c); return rc; };
     if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
@@ -477,6 +507,7 @@ void dra_ctx_destroy(dra_ctx* c) {
     for (int r = 0; r < (int)PEER_MAX; ++r) if (c->peer_base[r] && c->peer_base[r] != c->peer_local) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->peer_local) cudaFree(c->peer_local);
     if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_gbar) cudaFree(c->d_gbar);
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
                    c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels};
@@ -628,6 +659,52 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
     const bool direct = rb && is_pinned(out, rb);
     if (rb && !direct && (rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, rb))) return rc;
     void* dst_o = direct ? (void*)out : (void*)ctx->h_out;
+
+    // Direct host I/O: when the batch takes the single-launch kernel with the claim array staged in shared memory
+    // and all its CTAs can be resident at once, the kernel itself reads the claims from the (pinned, device-mapped)
+    // host buffer and writes the OutRecs back there — no copy-engine transfers, no graph, one cooperative launch.
+    {
+        static const bool no_direct = getenv("DRA_NO_DIRECT") != nullptr;
+        const FusedPlan plan = fused_plan(ctx, n_claim, flags);
+        bool ok = !no_direct && !(ctx->cfg_flags & DRA_CFG_NO_DIRECT) && ctx->coop_ok && plan.fused && plan.stage && n_claim && rb &&
+                  !ctx->profiling && ((uintptr_t)src_c & 15) == 0 && ((uintptr_t)dst_o & 15) == 0 &&
+                  (!src_o || ((uintptr_t)src_o & 3) == 0);
+        if (ok && ctx->dio_cap_smem != (int)plan.smem) {
+            // co-resident capacity at this shared-memory size (the attribute must be raised before the query)
+            if (plan.smem > 48 * 1024 && ctx->fused_smem_set_stage < (int)plan.smem) {
+                CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+                ctx->fused_smem_set_stage = (int)plan.smem;
+            }
+            int nb = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, true, 1>, FUSED_NW * 32, plan.smem));
+            ctx->dio_cap_smem = (int)plan.smem; ctx->dio_cap_cta = nb * ctx->n_sm;
+        }
+        ok = ok && (int)(ctx->n_node + 1) <= ctx->dio_cap_cta;
+        if (ok) {
+            // the host pointers must be usable by the device as they are (UVA identity mapping); checked once each
+            const void* hp[3] = {src_c, src_o, dst_o};
+            for (int k = 0; k < 3 && ok; ++k) {
+                if (!hp[k] || ctx->dio_seen[k] == hp[k]) continue;
+                void* dp = nullptr;
+                if (cudaHostGetDevicePointer(&dp, const_cast<void*>(hp[k]), 0) != cudaSuccess || dp != hp[k]) { (void)cudaGetLastError(); ok = false; }
+                else ctx->dio_seen[k] = hp[k];
+            }
+        }
+        if (ok && !ctx->d_gbar) { CU(cudaMalloc((void**)&ctx->d_gbar, 64)); CU(cudaMemsetAsync(ctx->d_gbar, 0, 64, ctx->stream)); }
+        if (ok) {
+            DirectIO d;
+            d.h_claims = (const uint4*)src_c; d.h_out_off = (const uint32_t*)src_o; d.h_out = (uint2*)dst_o;
+            d.d_claims = ctx->d_claims; d.d_out_off = ctx->d_out_off; d.gbar = ctx->d_gbar;
+            ctx->dio_pending = d;
+            rc = launch_allocate(ctx, ctx->d_claims, n_claim, out_off ? ctx->d_out_off : nullptr, ctx->d_out, n_out, flags);
+            ctx->dio_pending = DirectIO{};
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(ctx->stream));
+            if ((rc = check_err(ctx))) return rc;
+            if (rb && !direct) memcpy(out, ctx->h_out, rb);
+            return DRA_OK;
+        }
+    }
 
     // DRA_CFG_USE_GRAPH: H2D -> kernel chain -> D2H replayed as ONE cudaGraphLaunch when the call has the same
     // shape and buffers as the previous one (the first call of a shape runs eagerly: it also sets the kernels'

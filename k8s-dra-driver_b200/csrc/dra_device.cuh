@@ -770,6 +770,18 @@ struct PeerTail {
     uint32_t world, rank, n_per16, epoch;
 };
 
+// Direct host I/O of the single-launch kernel (k_fused): the CTAs themselves ingest the batch from the caller's
+// pinned (device-mapped) host buffers and write the OutRecs back there, instead of copy-engine transfers around the
+// kernel.  Needs every CTA resident at once (cooperative launch): two grid-wide barriers.
+struct DirectIO {
+    const uint4* h_claims;        // NULL: off
+    const uint32_t* h_out_off;    // or NULL
+    uint2* h_out;
+    uint4* d_claims;              // device copies the kernel body reads (= PackArgs::claims / out_off)
+    uint32_t* d_out_off;
+    uint32_t* gbar;               // [0] arrival count, [1] generation (self-resetting, reusable across launches)
+};
+
 struct PackArgs {
     const uint4* sorted;          // node-sorted claims, .y = first out slot          (k_pack)
     const uint32_t* claim_off;    // [n_node+2]                                        (k_pack)
@@ -786,6 +798,7 @@ struct PackArgs {
     SelCtx sel;                   // optional GPU attributes + selector table (spec §10)
     PeerTail peer;                // world == 0: single GPU                            (k_fused)
     unsigned long long* timeline; // optional instrumentation: 8 clock stamps per CTA  (k_fused), else NULL
+    DirectIO dio;                 //                                                   (k_fused)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
@@ -1266,7 +1279,7 @@ struct IdxGet {            // claim m of the node, through the index lists
     __device__ __forceinline__ uint4 operator()(uint32_t m) const {
         const uint32_t i = index_of(m);
         uint4 c = stage_addr ? lds128(stage_addr + (i << 4)) : __ldg(&claims[i]);
-        c.y = out_off ? __ldg(&out_off[i]) : i;
+        c.y = out_off ? __ldcg(&out_off[i]) : i;
         return c;
     }
 };
@@ -1274,6 +1287,7 @@ struct IdxGet {            // claim m of the node, through the index lists
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
 }
+#define DRA_DSTAMP(k) do { if (a.timeline && blockIdx.x == 0 && threadIdx.x == 0) a.timeline[(a.n_node + 2) * 8 + (k)] = globaltimer_ns(); } while (0)
 #define DRA_STAMP(k) do { if (a.timeline && threadIdx.x == 0) a.timeline[blockIdx.x * 8 + (k)] = (k) == 0 ? globaltimer_ns() : (unsigned long long)clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -1284,6 +1298,33 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 __device__ __forceinline__ void tma_load_multicast(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar, uint16_t mask) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
                  ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+
+// Grid-wide barrier for a cooperative launch (all CTAs resident).  Sense-free: the last arriver resets the count
+// and bumps the generation the others spin on, so the two words are reusable across barriers and launches.
+// bar.sync orders the CTA's earlier stores before thread 0's fence (fences are cumulative); a bounded spin turns a
+// lost CTA into an error flag instead of a hang.
+__device__ __forceinline__ void grid_barrier(uint32_t* gbar, uint32_t n_cta, const Err& err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(gbar + 1) : "memory");
+        __threadfence();
+        if (atomicAdd(gbar, 1u) == n_cta - 1) {
+            gbar[0] = 0;
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gbar + 1), "r"(gen + 1) : "memory");
+        } else {
+            const long long t0 = clock64();
+            uint32_t v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gbar + 1) : "memory");
+                if (v != gen) break;
+                if (clock64() - t0 > 400000000ll) { err.set(ERR_PEER_TIMEOUT); break; }
+            } while (true);
+        }
+    }
+    __syncthreads();
 }
 
 // CL = thread-block cluster size (1 or 8).  With CL = 8 the staged claim array is fetched from L2 ONCE per
@@ -1314,6 +1355,20 @@ k_fused(const PackArgs a) {
     if (threadIdx.x == 0) tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
     const uint32_t ng = g1 - g0;
     if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
+    if (STAGE && CL == 1 && a.dio.h_claims) {
+        // direct ingest: one 16-byte load from the caller's pinned buffer per thread (a single PCIe round trip for
+        // the whole grid), stored to the device copy that everybody's bulk copies below read from L2.
+        // (Per-piece ready flags instead of the grid barrier were tried: slower, 8.1 vs 5.8 us to the first bulk
+        // copy — every producer then pays its own fence on the critical path.)
+        DRA_DSTAMP(0);
+        const uint32_t nthr = gridDim.x * (NW * 32), t0 = blockIdx.x * (NW * 32) + threadIdx.x;
+        for (uint32_t i = t0; i < a.n_claim; i += nthr) a.dio.d_claims[i] = __ldcs(a.dio.h_claims + i);
+        if (a.dio.h_out_off) for (uint32_t i = t0; i < a.n_claim; i += nthr) a.dio.d_out_off[i] = __ldcs(a.dio.h_out_off + i);
+        DRA_DSTAMP(1);
+        grid_barrier(a.dio.gbar, gridDim.x, a.err);
+        asm volatile("fence.proxy.async;" ::: "memory");       // generic-proxy stores (other SMs) -> bulk-copy reads
+        DRA_DSTAMP(2);
+    }
     if (STAGE) {
         if (CL > 1) { cluster_arrive(); cluster_wait(); }      // barriers initialised in every CTA of the cluster before any multicast
         // every warp arms (and, for the pieces this CTA is responsible for, issues) its share of the pieces:
@@ -1343,9 +1398,9 @@ k_fused(const PackArgs a) {
     if (node == a.n_node) {
         // claims that name no node of the inventory: INVALID (spec §3); no state is touched
         for (uint32_t i = threadIdx.x; i < a.n_claim; i += NW * 32) {
-            const uint4 c = __ldg(&a.claims[i]);
+            const uint4 c = __ldcg(&a.claims[i]);              // L2: direct mode wrote the copy inside this kernel
             if (c.y < a.n_node) continue;
-            const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
+            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
             const uint32_t kind = c.x & 0xFFu;
             const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
             if (dst < a.n_out) {
@@ -1459,6 +1514,22 @@ k_fused(const PackArgs a) {
         }
     }
     if (CL > 1) cluster_wait();                    // nobody leaves while a cluster peer may still be receiving multicasts
+    if (STAGE && CL == 1 && a.dio.h_claims) {
+        // direct egress: when every CTA's OutRecs are in the device buffer, the grid writes them to the caller's
+        // pinned buffer as coalesced 16-byte stores (a scattered 8-byte store per record is what makes plain
+        // zero-copy output slow: profiles/e2e_parts_r01e.txt)
+        DRA_DSTAMP(3);
+        grid_barrier(a.dio.gbar, gridDim.x, a.err);
+        DRA_DSTAMP(4);
+        const uint32_t nthr = gridDim.x * (NW * 32), t0 = blockIdx.x * (NW * 32) + threadIdx.x;
+        const uint32_t n16 = a.n_out >> 1;
+        const uint4* src = reinterpret_cast<const uint4*>(a.out);
+        uint4* dst = reinterpret_cast<uint4*>(a.dio.h_out);
+        for (uint32_t i = t0; i < n16; i += nthr) __stcs(dst + i, __ldcg(src + i));
+        if ((a.n_out & 1u) && t0 == 0) a.dio.h_out[a.n_out - 1] = __ldcg(a.out + a.n_out - 1);
+        DRA_DSTAMP(5);
+        return;
+    }
     if (a.peer.world == 0) return;
 
     // ---- multi-GPU tail: all-gather by peer stores, fused here (no extra launch) -------------------------
@@ -1469,7 +1540,7 @@ k_fused(const PackArgs a) {
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
             const uint4 c = STAGE ? lds128(stage_addr + (i << 4)) : __ldg(&a.claims[i]);
-            const uint32_t dst = a.out_off ? __ldg(&a.out_off[i]) : i;
+            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
             const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
             const uint32_t slots = (kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
             if (dst > a.n_out || slots > a.n_out - dst) continue;

@@ -31,3 +31,18 @@ print("claims/node median %d max %d; live records/node median %d max %d" % (np.m
 print("inside pack: pre-pass median %d  serial loop median %d (%.0f cycles/live record)  epilogue median %d" % (np.median(pre), np.median(loop), np.median(loop / np.maximum(nlive, 1)), np.median(epi)))
 print("  pre-pass part a (validity/range/dead-shape emission) median %d; next-segment fetch median %d; pack minus (pre+loop+epi+fetch) median %d" % (np.median(pre_a), np.median(fetch), np.median((node[:, 6] - node[:, 5]).astype(np.int64) - pre - loop - epi - fetch)))
 i = int(np.argmax(tot)); print("slowest CTA", i, "pack", int(node[i, 6] - node[i, 5]), "pre/loop/epi", int(pre[i]), int(loop[i]), int(epi[i]), "claims", int(cnt[i]), "live", int(nlive[i]))
+
+# ---- direct host I/O (the host call): phases of CTA 0 in wall-clock ns (globaltimer) ----
+pin_c = pkg.api.PinnedBuffer(w.n_claim, pkg.records.CLAIM_DTYPE); pin_c.array[:] = w.claims
+pin_o = pkg.api.PinnedBuffer(w.n_out, pkg.records.OUT_DTYPE)
+import time
+for it in range(6):
+    flush.fill_(1); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.allocate_raw(pin_c.ptr, w.n_claim, None, pin_o.ptr, w.n_out, pkg.api.F_FRESH_INVENTORY)
+    dt = time.perf_counter() - t0
+tl = ctx.debug_timeline(w.n_node + 3).astype(np.uint64)
+d = tl[w.n_node + 2].astype(np.int64)
+if d[0]:
+    print("direct host I/O, CTA 0 (ns): ingest loads+stores %d | barrier 1 %d | body %d | barrier 2 (wait for the slowest CTA) %d | egress %d | total %d ; host call %.1f us"
+          % (d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4], d[5] - d[0], dt * 1e6))

@@ -39,12 +39,15 @@ GOLDEN_CASES = ["gpu_test4", "cfg1", "cfg2_small", "cfg4_small", "cfg5_small", "
                 "mixed3", "mixed11_valid"]
 
 
-@pytest.fixture(scope="session", params=["auto", "bucket+pack"])
+@pytest.fixture(scope="session", params=["auto", "copy-engine", "bucket+pack"])
 def ctx(pkg, request):
     """One CUDA context per kernel path for the GPU tests (fails loudly when the library or the device is
-    missing): "auto" takes the single-launch fused kernel whenever the batch is small enough,
-    "bucket+pack" forces the stable counting sort + pack chain."""
-    c = pkg.api.Context(device=0, flags=0 if request.param == "auto" else pkg.api.CFG_NO_FUSED)
+    missing): "auto" takes the single-launch fused kernel whenever the batch is small enough, with direct host
+    I/O (the kernel reads / writes the pinned host buffers itself) where that applies; "copy-engine" is the same
+    without direct host I/O (H2D / D2H copies around the kernel); "bucket+pack" forces the stable counting sort +
+    pack chain."""
+    flags = {"auto": 0, "copy-engine": pkg.api.CFG_NO_DIRECT, "bucket+pack": pkg.api.CFG_NO_FUSED}[request.param]
+    c = pkg.api.Context(device=0, flags=flags)
     c.path = request.param
     yield c
     c.close()

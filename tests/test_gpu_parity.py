@@ -216,7 +216,7 @@ def test_launch_counter_counts_our_kernels(pkg, ctx):
     ctx.set_table(w.table); ctx.set_inventory(w.gpus, w.node_off)
     before = ctx.launch_count()
     ctx.allocate(w.claims)
-    assert ctx.launch_count() - before == (1 if ctx.path == "auto" else 2)   # fused | bucket_small, pack
+    assert ctx.launch_count() - before == (2 if ctx.path == "bucket+pack" else 1)   # fused | bucket_small, pack
     ctx.set_inventory(w.gpus, w.node_off)
     before = ctx.launch_count()
     ctx.allocate(w.node_sorted().claims, flags=pkg.api.F_NODE_SORTED)
