@@ -1388,6 +1388,23 @@ k_fused(const PackArgs a) {
     }
     DRA_STAMP(2);
 
+    // warp 0 sets up the node (inventory, table row properties) NOW: it needs only the table and the GpuRecs, which
+    // land long before the claim pieces — after the filter this would sit on the critical path
+    NodeCtx x;
+    uint4 rec = make_uint4(0, 0, 0, 0);
+    if (wid == 0 && has_node) {
+        x.lane = lane; x.ltmask = lanemask_lt();
+        x.live_addr = sbase + FU_LIVE; x.tbl_addr = sbase + FU_TBL;
+        x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + FU_TBL);
+        x.have_off = a.have_off != 0;
+        x.sc = a.sel;
+        x.sink = OutSink{a.out, a.n_out, a.err, lane};
+        x.g0 = g0;
+        mbar_wait_a(tbar, 0);
+        if (ng) { mbar_wait_a(ibar, 0); if (lane < ng) rec = lds128(sbase + FU_INV + lane * 16); }
+        x.begin(rec, lane < ng);
+    }
+
     // ---- filter: which claims select this node (all warps) ------------------------------------------
     const uint32_t chunk = fused_chunk(a.n_claim, NW, STAGE);          // per-warp part
     const uint32_t lo = wid * chunk, hi = min(a.n_claim, lo + chunk);
@@ -1480,18 +1497,6 @@ k_fused(const PackArgs a) {
             uint4 c_cur; bool p_cur;
             fetch(0, c_cur, p_cur);
 
-            NodeCtx x;
-            x.lane = lane; x.ltmask = ltmask;
-            x.live_addr = sbase + FU_LIVE; x.tbl_addr = sbase + FU_TBL;
-            x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + FU_TBL);
-            x.have_off = a.have_off != 0;
-            x.sc = a.sel;
-            x.sink = OutSink{a.out, a.n_out, a.err, lane};
-            x.g0 = g0;
-            mbar_wait_a(tbar, 0);
-            uint4 rec = make_uint4(0, 0, 0, 0);
-            if (ng) { mbar_wait_a(ibar, 0); if (lane < ng) rec = lds128(sbase + FU_INV + lane * 16); }
-            x.begin(rec, lane < ng);
             x.prof_on = a.timeline != nullptr;
             DRA_STAMP(5);
 
