@@ -6,11 +6,15 @@
 A "step" is one Allocate batch: 10,000 mixed 1g/2g/3g/7g MIG claims (generation order, NOT node-sorted)
 over 125 nodes x 8 GPUs, evaluated against the freshly loaded inventory (BASELINE.md cfg2 = configs[1]).
 At N GPUs every rank owns such a shard (weak scaling: N x 10k claims over N x 1k GPUs, nodes sharded
-whole) and the step ends with the path's one collective, an all-gather of the OutRecs over NCCL.
+whole) and the step ends with the path's one collective, an all-gather of the OutRecs (NVLink peer stores
+fused into the kernel's tail; --nccl: ncclAllGather).
 
 value   = whole-job allocations/s with inputs resident in HBM (CUDA events on the launch stream, L2
           flushed between steps, max over ranks)
-e2e     = the same through the C-ABI host call: pinned host claims -> H2D -> kernels -> D2H OutRecs
+e2e     = the same through the C-ABI host call dra_allocate_batch with pinned host buffers, every step moving the
+          160 KB of claims host -> device and the 80 KB of OutRecs device -> host inside the timed region: by the
+          kernel itself (direct host I/O: one cooperative launch reads / writes the pinned buffers), or with
+          --no-direct by copy-engine transfers around it (H2D -> kernels -> D2H as one CUDA graph)
 roofline= algorithmic bytes of the batch / device time of the dominant kernel, vs MEASURED_PEAKS.json
 cpu_baseline / --impl reference = the CPU oracle of the same spec on the host cores (kind "port": the
           reference's Go allocator does not exist in the snapshot; no Go toolchain)
