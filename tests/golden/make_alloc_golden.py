@@ -44,6 +44,10 @@ def cases():
     for seed in range(4):
         yield S.mixed(800, 13, seed)
     w = S.mixed(300, 5, 11, invalid=False); w.name = "mixed11_valid"; yield w
+    # homogeneous all-MIG nodes: the packers' fast loops (<= 8 and > 8 GPUs per node, 8- and 16-slice parts)
+    w = S.homog(900, 6, 0, max_width=8); w.name = "homog_w8"; yield w
+    w = S.homog(1500, 7, 1, max_width=32); w.name = "homog_w32"; yield w
+    w = S.homog(1200, 6, 4, wide16=True, max_width=32); w.name = "homog_16slice"; yield w
 
 
 def main():
