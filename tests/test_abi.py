@@ -79,6 +79,46 @@ def test_kernels_are_sm100a_and_use_tma(pkg):
         assert mnem in r.stdout, mnem
 
 
+def test_flag_constants_match_header(pkg):
+    """DRA_CFG_* / DRA_F_* / error codes of the ctypes binding are the header's."""
+    text = open(HEADER).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(DRA_(?:CFG|F)_[A-Z_]+)\s+(0x[0-9a-fA-F]+)u", text)}
+    A = pkg.api
+    assert defs == {"DRA_CFG_USE_GRAPH": A.CFG_USE_GRAPH, "DRA_CFG_NO_FUSED": A.CFG_NO_FUSED,
+                    "DRA_CFG_NO_DIRECT": A.CFG_NO_DIRECT, "DRA_F_NODE_SORTED": A.F_NODE_SORTED,
+                    "DRA_F_FRESH_INVENTORY": A.F_FRESH_INVENTORY}
+    errs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(DRA_E_[A-Z]+)\s+\((-\d+)\)", text)}
+    assert errs == {"DRA_E_INVAL": A.E_INVAL, "DRA_E_CUDA": A.E_CUDA, "DRA_E_NCCL": A.E_NCCL, "DRA_E_NOMEM": A.E_NOMEM,
+                    "DRA_E_STATE": A.E_STATE}
+
+
+def test_packer_context_stays_in_registers(pkg):
+    """The packing kernels keep the node context (lane state, memo, sink) in registers: a reference into it handed
+    to the out-of-line generic step once pinned the whole context in local memory (STACK 208, an LDL on every access
+    of the hot loops).  What remains on the stack are the copies made for that call.  Also: the sort path's
+    dependent-launch instructions and the warp reductions of the lean loops are in the SASS."""
+    so = pkg.api.SO_PATH
+    r = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    stacks = {}
+    name = None
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"STACK:(\d+)", line)
+        if m and name:
+            stacks[name] = int(m.group(1))
+    hot = {k: v for k, v in stacks.items() if "k_fused" in k or "k_pack" in k}
+    assert len(hot) >= 4, stacks
+    assert all(v <= 96 for v in hot.values()), hot
+    assert all(v == 0 for k, v in stacks.items() if k not in hot), stacks
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    for mnem in ("PREEXIT", "ACQBULK", "REDUX.OR", "CREDUX.MIN"):
+        assert mnem in sass, mnem
+
+
 def test_synthetic_configs_shape(pkg):
     S = pkg.synth
     w = S.cfg2()
