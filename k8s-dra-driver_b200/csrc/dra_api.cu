@@ -263,8 +263,9 @@ FusedPlan fused_plan(const dra_ctx* ctx, uint32_t n_claim, uint32_t flags) {
     p.stage = !no_stage && n_claim <= FUSED_NW * FU_PIECE * FU_MAXPIECE && fused_smem_bytes(n_claim, FUSED_NW, true) <= 225 * 1024;
     p.smem = fused_smem_bytes(n_claim, FUSED_NW, p.stage);
     // Measured crossover against the sort path (profiles/path_crossover_r01f.txt): the single launch costs about
-    // 4 us + 1.2 us per 1000 claims while all CTAs fit one wave, the sort path 23 us + 0.25 us per 1000 claims.
-    const uint32_t fused_max_claims = n_node + 1 <= 148 ? 20000u : 12000u;
+    // 4 us + 1.2 us per 1000 claims while all CTAs fit one wave (10 us + 1.4 us beyond), the sort path about
+    // 20 us + 0.2 us per 1000 claims.
+    const uint32_t fused_max_claims = n_node + 1 <= 148 ? 14000u : 7500u;
     p.fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) && n_claim <= fused_max_claims &&
               (uint64_t)n_node * n_claim <= ctx->fused_max_work && p.smem <= 225 * 1024 && n_node <= 16384;
     return p;
@@ -389,7 +390,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
                 if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
                 k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank);
                 prof.mark();
-                CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 255) / 256), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
+                CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 7) / 8), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
                 prof.mark();
             } else {
                 size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);

@@ -514,25 +514,36 @@ k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_no
     }
 }
 
-// k_bucket_scan8: grid = ceil((n_node+1)/256) CTAs, thread per node.  In place: hist[t][n] <- sum_{t'<t}; node totals
-// go to claim_off[n]; the LAST CTA to finish (ticket) turns the totals into the exclusive offsets.
+// k_bucket_scan8: grid = ceil((n_node+1)/8) CTAs of 8 warps, WARP per node, lanes over the tiles: every load of a
+// node's column is in flight at once (the thread-per-node form walked the tiles in 7 dependent L2 round trips on 4
+// SMs), the prefix over the tiles is a warp scan by shuffles.  In place: hist[t][n] <- sum_{t'<t}; node totals go to
+// claim_off[n]; the LAST CTA to finish (ticket) turns the totals into the exclusive offsets.
 __global__ void __launch_bounds__(256)
 k_bucket_scan8(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node, uint32_t* __restrict__ claim_off,
                uint32_t* __restrict__ ticket) {
     const uint32_t nb = n_node + 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     pdl_trigger(); pdl_wait();
-    const uint32_t n = blockIdx.x * 256 + tid;
+    const uint32_t n = blockIdx.x * 8 + wid;
     if (n < nb) {
-        uint32_t run = 0, t = 0;
-        for (; t + 8 <= n_tiles; t += 8) {
-            uint32_t v[8];
+        uint32_t run = 0;
+        for (uint32_t t0 = 0; t0 < n_tiles; t0 += 128) {                   // 4 tiles per lane and round
+            uint32_t v[4], x[4];
             #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = hist[(size_t)(t + q) * nb + n];
+            for (int q = 0; q < 4; ++q) { const uint32_t t = t0 + q * 32 + lane; v[q] = t < n_tiles ? __ldcg(&hist[(size_t)t * nb + n]) : 0u; }
             #pragma unroll
-            for (int q = 0; q < 8; ++q) { hist[(size_t)(t + q) * nb + n] = run; run += v[q]; }
+            for (int q = 0; q < 4; ++q) {
+                x[q] = v[q];
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, x[q], d); if (lane >= (uint32_t)d) x[q] += y; }
+            }
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t t = t0 + q * 32 + lane;
+                if (t < n_tiles) hist[(size_t)t * nb + n] = run + x[q] - v[q];
+                run += __shfl_sync(FULLMASK, x[q], 31);
+            }
         }
-        for (; t < n_tiles; ++t) { const uint32_t v = hist[(size_t)t * nb + n]; hist[(size_t)t * nb + n] = run; run += v; }
-        claim_off[n] = run;
+        if (lane == 0) claim_off[n] = run;
     }
     __threadfence();
     __shared__ uint32_t last_s, wsum[8], carry_s, total_s;
