@@ -332,3 +332,26 @@ def test_adjacent_integer_searches(pkg, ctx, oracle):
     assert list(got) == [oracle.imex_offset(d) for d in doms]
     wide = ctx.imex_offsets([list(range(0, 64 * 10, 10))], step=10, limit=1000)      # more than 32 windows
     assert wide[0] == oracle.imex_offset(list(range(0, 640, 10)), step=10, limit=1000) == 640
+
+
+# ---- property-based: arbitrary small problems (random placement tables with odd sizes and arbitrary start masks,
+# ragged blocked / pre-occupied inventories, every claim kind incl. malformed ones and co-location runs) -----------
+def test_cuda_matches_oracle_on_arbitrary_problems(pkg, ctx, oracle):
+    from hypothesis import HealthCheck, given, settings
+    from test_oracle_properties import problems
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(problems())
+    def run(prob):
+        g, off, t, c, out_off, n_out = prob
+        ctx.set_table(t)
+        ctx.set_inventory(g, off)
+        out = ctx.allocate(c, out_off, n_out)
+        inv = ctx.get_inventory()
+        ref_out, ref_inv = oracle.allocate(g, off, t, c, out_off, n_out)
+        _assert_same(out, inv, ref_out, ref_inv, "arbitrary problem")
+        if len(c):                                         # Deallocate (spec §9) on the device: back to the start
+            ctx.deallocate(c, out, out_off)
+            assert ctx.get_inventory().tobytes() == g.tobytes()
+
+    run()
