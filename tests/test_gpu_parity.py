@@ -346,6 +346,16 @@ def test_cuda_matches_oracle_on_arbitrary_problems(pkg, ctx, oracle):
         g, off, t, c, out_off, n_out = prob
         ctx.set_table(t)
         ctx.set_inventory(g, off)
+        if len(c):                                         # UnsuitableNodes first (pure): every pod x every node
+            cut = [i for i in range(1, len(c)) if c["group"][i] == 0 or c["group"][i] != c["group"][i - 1]]
+            pod_off = np.array([0] + cut[::2] + [len(c)], dtype=np.uint32)     # pods never split a co-location run
+            n_pod, n_node = len(pod_off) - 1, len(off) - 1
+            bits = ctx.unsuitable(c, pod_off)
+            cand_nodes = np.tile(np.arange(n_node, dtype=np.uint32), n_pod)
+            cand_off = (np.arange(n_pod + 1, dtype=np.uint32) * n_node).astype(np.uint32)
+            ref_bits = oracle.unsuitable(g, off, t, c, pod_off, cand_nodes, cand_off)
+            assert bits[: len(ref_bits)].tobytes() == ref_bits.tobytes(), "UnsuitableNodes differs"
+            assert ctx.get_inventory().tobytes() == g.tobytes()
         out = ctx.allocate(c, out_off, n_out)
         inv = ctx.get_inventory()
         ref_out, ref_inv = oracle.allocate(g, off, t, c, out_off, n_out)
