@@ -295,6 +295,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     const size_t fused_smem = plan.smem;
     const DirectIO dio = ctx->dio_pending;
     ctx->dio_pending = DirectIO{};
+    if (dio.h_claims && !(fused && stage)) return fail(ctx, DRA_E_STATE, "direct host I/O was planned for a batch that does not take the staged single-launch kernel");
     if (fused) {
         if (tail) { a.peer = *tail; if (tail_done) *tail_done = true; }
         // clusters of 8 CTAs + TMA multicast when the array is staged and there are enough nodes to share it
