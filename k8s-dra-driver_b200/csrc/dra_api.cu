@@ -666,7 +666,7 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
     // and all its CTAs can be resident at once, the kernel itself reads the claims from the (pinned, device-mapped)
     // host buffer and writes the OutRecs back there — no copy-engine transfers, no graph, one cooperative launch.
     {
-        static const bool no_direct = getenv("DRA_NO_DIRECT") != nullptr;
+        static const bool no_direct = getenv("DRA_NO_DIRECT") != nullptr || getenv("DRA_CLUSTER") != nullptr;   // (the cluster experiment has no ingest)
         const FusedPlan plan = fused_plan(ctx, n_claim, flags);
         bool ok = !no_direct && !(ctx->cfg_flags & DRA_CFG_NO_DIRECT) && ctx->coop_ok && plan.fused && plan.stage && n_claim && rb &&
                   !ctx->profiling && ((uintptr_t)src_c & 15) == 0 && ((uintptr_t)dst_o & 15) == 0 &&
