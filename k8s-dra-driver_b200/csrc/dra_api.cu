@@ -857,7 +857,7 @@ int dra_deallocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
     if (ob) CU(cudaMemcpyAsync(ctx->d_out_off, ctx->h_in + cb, ob, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_out, ctx->h_in + cb + ob, rb, cudaMemcpyHostToDevice, ctx->stream));
     k_dealloc<<<(n_claim + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_claims, n_claim, out_off ? ctx->d_out_off : nullptr,
-                                                             ctx->d_out, n_out, (uint32_t*)ctx->d_inv_live, ctx->n_gpu, err_of(ctx));
+                                                             ctx->d_out, n_out, (uint32_t*)ctx->d_inv_live, ctx->n_gpu, ctx->n_node, err_of(ctx));
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
     cudaError_t e = cudaGetLastError();

@@ -1652,14 +1652,15 @@ k_unsuitable(const UnsArgs a) {
 __global__ void __launch_bounds__(256)
 k_dealloc(const uint4* __restrict__ claims, uint32_t n_claim, const uint32_t* __restrict__ out_off,
           const uint2* __restrict__ out, uint32_t n_out, uint32_t* __restrict__ inv, uint32_t n_gpu,
-          Err err) {
+          uint32_t n_node, Err err) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_claim) return;
     const uint4 c = __ldg(&claims[i]);
     const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
     const bool have_off = out_off != nullptr;
     const uint32_t base = have_off ? __ldg(&out_off[i]) : i;
-    const uint32_t slots = (kind == DRA_KIND_GPU && count >= 1 && count <= DRA_MAX_COUNT &&
+    // slots(c) exactly as Allocate counted them (spec §9): an INVALID claim — here: one naming no node — has one
+    const uint32_t slots = (kind == DRA_KIND_GPU && c.y < n_node && count >= 1 && count <= DRA_MAX_COUNT &&
                             (have_off || count == 1)) ? count : 1u;
     if (base > n_out || slots > n_out - base) { err.set(ERR_OUT_RANGE); return; }
     for (uint32_t s = 0; s < slots; ++s) {

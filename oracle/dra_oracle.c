@@ -474,7 +474,7 @@ int dra_oracle_unsuitable(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_
 }
 
 /* spec §9 */
-int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu,
+int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu, uint32_t n_node,
                           const dra_claim_rec* claims, uint32_t n_claim,
                           const uint32_t* out_off, const dra_out_rec* out, uint32_t n_out)
 {
@@ -482,7 +482,8 @@ int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu,
     for (uint32_t i = 0; i < n_claim; i++) {
         const dra_claim_rec* c = &claims[i];
         uint32_t base = have_off ? out_off[i] : i;
-        uint32_t sl = (c->kind == DRA_KIND_GPU && c->count >= 1 && c->count <= DRA_MAX_COUNT &&
+        /* slots(c) of spec §1/§3, the same as Allocate used: an INVALID claim (here: naming no node) has one */
+        uint32_t sl = (c->kind == DRA_KIND_GPU && c->node < n_node && c->count >= 1 && c->count <= DRA_MAX_COUNT &&
                        (have_off || c->count == 1)) ? c->count : 1;
         if (base > n_out || sl > n_out - base) return -1;
         for (uint32_t k = 0; k < sl; k++) {

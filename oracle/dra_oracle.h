@@ -43,7 +43,7 @@ int dra_oracle_unsuitable(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_
                           const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits);
 
 /* Deallocate (spec §9). */
-int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu,
+int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu, uint32_t n_node,
                           const dra_claim_rec* claims, uint32_t n_claim,
                           const uint32_t* out_off, const dra_out_rec* out, uint32_t n_out);
 

@@ -48,7 +48,7 @@ def lib():
         _lib.dra_oracle_allocate_mt.restype = i32
         _lib.dra_oracle_unsuitable.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, u32, vp, vp, vp]
         _lib.dra_oracle_unsuitable.restype = i32
-        _lib.dra_oracle_deallocate.argtypes = [vp, u32, vp, u32, vp, vp, u32]
+        _lib.dra_oracle_deallocate.argtypes = [vp, u32, u32, vp, u32, vp, vp, u32]
         _lib.dra_oracle_deallocate.restype = i32
         _lib.dra_oracle_set_selectors.argtypes = [vp, u32, vp, u32]
         _lib.dra_oracle_set_selectors.restype = None
@@ -102,12 +102,15 @@ def unsuitable(gpus, node_off, table, claims, pod_off, cand_nodes, cand_off):
     return bits[: (n_pair + 7) // 8]
 
 
-def deallocate(gpus, claims, out, out_off=None):
+def deallocate(gpus, claims, out, out_off=None, n_node=None):
+    """n_node: number of nodes of the inventory (claims naming no node have one slot, spec §9); None = every node
+    index is taken as valid."""
     g = _c(gpus, GPU_DTYPE).copy()
     c = _c(claims, CLAIM_DTYPE)
     o = _c(out, OUT_DTYPE)
     oo = None if out_off is None else _c(out_off, np.uint32)
-    rc = lib().dra_oracle_deallocate(_p(g), len(g), _p(c), len(c), _p(oo), _p(o), len(o))
+    rc = lib().dra_oracle_deallocate(_p(g), len(g), 0xFFFFFFFF if n_node is None else int(n_node), _p(c), len(c),
+                                     _p(oo), _p(o), len(o))
     if rc != 0:
         raise ValueError(f"dra_oracle_deallocate: rc={rc}")
     return g

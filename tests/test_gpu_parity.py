@@ -119,6 +119,23 @@ def test_edge_cases(pkg, ctx, oracle):
     _assert_same(out, inv, ref_out, ref_inv, "single hot node")
 
 
+def test_deallocate_counts_slots_like_allocate(pkg, ctx, oracle):
+    """A multi-count GPU claim that names no node has ONE (INVALID) slot in Allocate and in Deallocate (spec §9)."""
+    R = pkg.records
+    g, off = R.make_inventory([2], mig=False)
+    c = np.zeros(2, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_GPU
+    c["count"] = [1, 2]
+    c["node"] = [0, 1]
+    out_off, n_out = R.out_offsets(c, 1)
+    ctx.set_table(R.default_table()); ctx.set_inventory(g, off)
+    out = ctx.allocate(c, out_off, n_out)
+    ref_out, ref_inv = oracle.allocate(g, off, R.default_table(), c, out_off, n_out)
+    _assert_same(out, ctx.get_inventory(), ref_out, ref_inv, "invalid multi-count claim")
+    ctx.deallocate(c, out, out_off)                        # used to fail: slot count ran past n_out
+    assert ctx.get_inventory().tobytes() == g.tobytes()
+
+
 def test_out_off_out_of_range_is_an_error(pkg, ctx):
     R = pkg.records
     g, off = R.make_inventory([4], mig=False)
@@ -340,7 +357,9 @@ def test_cuda_matches_oracle_on_arbitrary_problems(pkg, ctx, oracle):
     from hypothesis import HealthCheck, given, settings
     from test_oracle_properties import problems
 
-    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    import os
+    n_ex = int(os.environ.get("DRA_PROP_EXAMPLES", "0"))      # > 0: that many RANDOM examples instead of the fixed 120
+    @settings(max_examples=n_ex or 120, deadline=None, suppress_health_check=list(HealthCheck), derandomize=n_ex == 0, database=None)
     @given(problems())
     def run(prob):
         g, off, t, c, out_off, n_out = prob

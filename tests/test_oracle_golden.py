@@ -153,8 +153,26 @@ def test_oracle_reproduces_golden(oracle, name):
 def test_deallocate_round_trip(pkg, oracle):
     w = pkg.synth.mixed(1500, 17, 3, invalid=False)
     out, after = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
-    back = oracle.deallocate(after, w.claims, out, w.out_off)
+    back = oracle.deallocate(after, w.claims, out, w.out_off, n_node=w.n_node)
     assert back.tobytes() == w.gpus.tobytes()
+
+
+def test_deallocate_counts_slots_like_allocate(pkg, oracle):
+    """Found by the property test: a multi-count GPU claim that names no node is INVALID and has ONE OutRec slot
+    (spec §1/§3); Deallocate must count its slots the same way (spec §9) — it used to assume `count` slots and ran
+    off the end of the result array (or looked at the next claim's record)."""
+    R = pkg.records
+    g, off = R.make_inventory([2], mig=False)
+    c = np.zeros(2, dtype=R.CLAIM_DTYPE)
+    c["kind"] = R.KIND_GPU
+    c["count"] = [1, 2]
+    c["node"] = [0, 1]                                    # the second claim names no node of the inventory
+    out_off, n_out = R.out_offsets(c, 1)
+    assert (list(out_off), n_out) == ([0, 1], 2)
+    out, after = oracle.allocate(g, off, R.default_table(), c, out_off, n_out)
+    assert [int(s) for s in out["status"]] == [R.ST_OK, R.ST_INVALID]
+    back = oracle.deallocate(after, c, out, out_off, n_node=1)
+    assert back.tobytes() == g.tobytes()
 
 
 def test_idempotent_when_full(pkg, oracle):
