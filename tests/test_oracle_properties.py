@@ -89,6 +89,24 @@ def test_oracle_agrees_with_naive_and_keeps_the_spec_invariants(pkg, oracle, pro
             elif c[i]["kind"] == R.KIND_GPU:
                 assert not (g["flags"][gi] & R.GPU_MIG_ENABLED)                   # GPU xor MIG parent (nvlib.go:152)
     assert (after["busy"].astype(np.int64) == busy).all()
+    # UnsuitableNodes (spec §8) from its definition, with the independent restatement: a pod is suitable on a node iff
+    # allocating just its claims there, on a snapshot, leaves every slot OK
+    if len(c):
+        cut = [i for i in range(1, len(c)) if c["group"][i] == 0 or c["group"][i] != c["group"][i - 1]]
+        pod_off = np.array([0] + cut[::2] + [len(c)], dtype=np.uint32)         # pods never split a co-location run
+        n_pod = len(pod_off) - 1
+        cand_nodes = np.tile(np.arange(n_node, dtype=np.uint32), n_pod)
+        cand_off = (np.arange(n_pod + 1, dtype=np.uint32) * n_node).astype(np.uint32)
+        bits = oracle.unsuitable(g, off, t, c, pod_off, cand_nodes, cand_off)
+        got = np.unpackbits(bits, bitorder="little")[: n_pod * n_node].reshape(n_pod, n_node)
+        gd, offl = _dicts(g), [int(x) for x in off]
+        for pd in range(n_pod):
+            pc = c[pod_off[pd]: pod_off[pd + 1]].copy()
+            for nd in range(n_node):
+                pc["node"] = nd
+                po, pn = R.out_offsets(pc, n_node)
+                res, _ = naive.allocate(gd, offl, tbl, _dicts(pc), [int(x) for x in po])
+                assert bool(got[pd, nd]) == all(r[4] == R.ST_OK for r in res[:pn]), (pd, nd)
     # Deallocate everything that was allocated: back to the start (spec §9)
     back = oracle.deallocate(after, c, out, out_off, n_node=n_node)
     assert back.tobytes() == g.tobytes()
