@@ -384,3 +384,36 @@ def test_cuda_matches_oracle_on_arbitrary_problems(pkg, ctx, oracle):
             assert ctx.get_inventory().tobytes() == g.tobytes()
 
     run()
+
+
+def test_cuda_selectors_match_oracle_on_arbitrary_problems(pkg, ctx, oracle):
+    """Random selector programs (well-formed trees and garbage), random attributes, every claim kind: the device's
+    predicate evaluation and its interplay with runs / the failure memo against the oracle (spec §10)."""
+    import os
+    from hypothesis import HealthCheck, given, settings
+    from test_oracle_selector_properties import selector_problems
+    R = pkg.records
+    n_ex = int(os.environ.get("DRA_PROP_EXAMPLES", "0"))
+
+    @settings(max_examples=n_ex or 100, deadline=None, suppress_health_check=list(HealthCheck), derandomize=n_ex == 0, database=None)
+    @given(selector_problems(), __import__("hypothesis").strategies.integers(0, 3))
+    def run(prob, every):
+        g, off, t, c, out_off, n_out, attrs, sels, sid = prob
+        cs = c.copy()                                      # every claim, or every 2nd / 3rd / 4th, carries the selector
+        pick = (np.arange(len(cs)) % (every + 1)) == 0
+        gm = pick & ((cs["kind"] == R.KIND_GPU) | (cs["kind"] == R.KIND_MIG))
+        cs["mem_limit_mib"] = np.where(gm, sid, cs["mem_limit_mib"])
+        cs["group"] = np.where(pick & (cs["kind"] == R.KIND_SHARED), sid, cs["group"])
+        ctx.set_table(t); ctx.set_inventory(g, off)
+        ctx.set_gpu_attrs(attrs); ctx.set_selectors(sels.reshape(-1, R.SEL_MAX_INS))
+        oracle.set_selectors(attrs, sels)
+        try:
+            out = ctx.allocate(cs, out_off, n_out)
+            inv = ctx.get_inventory()
+            ref_out, ref_inv = oracle.allocate(g, off, t, cs, out_off, n_out)
+            _assert_same(out, inv, ref_out, ref_inv, "selectors on an arbitrary problem")
+        finally:
+            oracle.set_selectors()
+            ctx.set_selectors(None); ctx.set_gpu_attrs(None)
+
+    run()
