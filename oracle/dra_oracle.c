@@ -370,7 +370,80 @@ static void run_nodes(const mt_arg* a)
     }
 }
 
-static void* mt_entry(void* p) { run_nodes((const mt_arg*)p); return NULL; }
+/* ---- persistent worker pool for the multi-threaded variant --------------------------------------------
+ * Nodes are independent (spec §2), a node costs microseconds: creating threads per call costs more than the
+ * batch, so the workers are created once, take nodes one at a time from an atomic counter, and wait for the next
+ * batch by spinning briefly before they sleep on a condition variable. */
+#include <stdatomic.h>
+#include <sched.h>
+
+static struct {
+    pthread_t* th; int n;                       /* workers (the caller works too) */
+    _Atomic uint64_t gen;                       /* batch generation */
+    _Atomic uint32_t next, done;                /* next node to take; workers finished with this generation */
+    const mt_arg* job;
+    _Atomic int stop, sleepers;
+    pthread_mutex_t mu; pthread_cond_t cv;
+} pool = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER };
+
+static void take_nodes(const mt_arg* a)
+{
+    for (;;) {
+        uint32_t n = atomic_fetch_add_explicit(&pool.next, 1u, memory_order_relaxed);
+        if (n >= a->n_node) return;
+        mt_arg one = *a; one.n0 = n; one.n1 = n + 1;
+        run_nodes(&one);
+    }
+}
+
+static void* pool_worker(void* unused)
+{
+    (void)unused;
+    uint64_t seen = 0;
+    for (;;) {
+        uint32_t spins = 0;
+        while (atomic_load_explicit(&pool.gen, memory_order_acquire) == seen && !atomic_load(&pool.stop)) {
+            if (++spins < 20000u) { __builtin_ia32_pause(); continue; }
+            pthread_mutex_lock(&pool.mu);                    /* idle for a while: sleep until the next batch */
+            atomic_fetch_add(&pool.sleepers, 1);
+            while (atomic_load_explicit(&pool.gen, memory_order_acquire) == seen && !atomic_load(&pool.stop))
+                pthread_cond_wait(&pool.cv, &pool.mu);
+            atomic_fetch_sub(&pool.sleepers, 1);
+            pthread_mutex_unlock(&pool.mu);
+        }
+        if (atomic_load(&pool.stop)) return NULL;
+        seen = atomic_load_explicit(&pool.gen, memory_order_acquire);
+        take_nodes(pool.job);
+        atomic_fetch_add_explicit(&pool.done, 1u, memory_order_release);
+    }
+}
+
+static void pool_shutdown(void)
+{
+    if (!pool.n) return;
+    pthread_mutex_lock(&pool.mu);
+    atomic_store(&pool.stop, 1);
+    pthread_cond_broadcast(&pool.cv);
+    pthread_mutex_unlock(&pool.mu);
+    for (int t = 0; t < pool.n; t++) pthread_join(pool.th[t], NULL);
+    free(pool.th); pool.th = NULL; pool.n = 0;
+    atomic_store(&pool.stop, 0);
+}
+
+static int pool_resize(int workers)
+{
+    if (workers == pool.n) return 0;
+    pool_shutdown();
+    if (workers <= 0) return 0;
+    pool.th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)workers);
+    if (!pool.th) return -1;
+    static int at_exit_set;
+    if (!at_exit_set) { atexit(pool_shutdown); at_exit_set = 1; }
+    for (int t = 0; t < workers; t++)
+        if (pthread_create(&pool.th[t], NULL, pool_worker, NULL)) { pool.n = t; pool_shutdown(); return -1; }
+    pool.n = workers;
+    return 0;
+}
 
 int dra_oracle_allocate_mt(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node,
                            const dra_profile_tbl* tbl,
@@ -393,25 +466,20 @@ int dra_oracle_allocate_mt(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* no
     if (bucket(claims, n_claim, n_node, &b)) return -1;
 
     mt_arg base = { gpus, node_off, n_node, tbl, claims, &b, out_off, out, 0, n_node };
-    if (n_threads <= 1 || n_node < 2) {
+    if ((uint32_t)n_threads > n_node) n_threads = (int)n_node;
+    if (n_threads <= 1 || n_node < 2 || pool_resize(n_threads - 1)) {
         run_nodes(&base);
     } else {
-        if ((uint32_t)n_threads > n_node) n_threads = (int)n_node;
-        pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
-        mt_arg* args = (mt_arg*)malloc(sizeof(mt_arg) * (size_t)n_threads);
-        /* contiguous node ranges balanced by claim count */
-        uint32_t n = 0;
-        for (int t = 0; t < n_threads; t++) {
-            args[t] = base;
-            args[t].n0 = n;
-            uint64_t target = (uint64_t)b.off[n_node] * (uint64_t)(t + 1) / (uint64_t)n_threads;
-            while (n < n_node && (b.off[n + 1] <= target || t == n_threads - 1)) n++;
-            if (t == n_threads - 1) n = n_node;
-            args[t].n1 = n;
-            pthread_create(&th[t], NULL, mt_entry, &args[t]);
+        /* the caller and n_threads-1 pool workers take nodes one at a time (dynamic balance) */
+        pool.job = &base;
+        atomic_store_explicit(&pool.next, 0u, memory_order_relaxed);
+        atomic_store_explicit(&pool.done, 0u, memory_order_relaxed);
+        atomic_fetch_add_explicit(&pool.gen, 1u, memory_order_release);
+        if (atomic_load(&pool.sleepers)) {
+            pthread_mutex_lock(&pool.mu); pthread_cond_broadcast(&pool.cv); pthread_mutex_unlock(&pool.mu);
         }
-        for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
-        free(th); free(args);
+        take_nodes(&base);
+        while (atomic_load_explicit(&pool.done, memory_order_acquire) != (uint32_t)pool.n) __builtin_ia32_pause();
     }
     free(b.idx); free(b.off);
     return 0;

@@ -25,7 +25,9 @@ int dra_oracle_allocate(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_
                         const dra_claim_rec* claims, uint32_t n_claim,
                         const uint32_t* out_off, dra_out_rec* out, uint32_t n_out);
 
-/* Same result, nodes processed by n_threads pthreads (nodes are independent, spec §2). */
+/* Same result, nodes processed by n_threads threads: the caller plus a persistent pool of n_threads-1 workers that
+ * take nodes one at a time (nodes are independent, spec §2).  The pool is created on first use and resized when
+ * n_threads changes; one call at a time. */
 int dra_oracle_allocate_mt(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node,
                            const dra_profile_tbl* tbl,
                            const dra_claim_rec* claims, uint32_t n_claim,
