@@ -430,6 +430,14 @@ static void pool_shutdown(void)
     atomic_store(&pool.stop, 0);
 }
 
+/* a forked child has none of the parent's worker threads: start from an empty pool there */
+static void pool_after_fork_child(void)
+{
+    pool.th = NULL; pool.n = 0;
+    atomic_store(&pool.stop, 0); atomic_store(&pool.sleepers, 0);
+    pthread_mutex_init(&pool.mu, NULL); pthread_cond_init(&pool.cv, NULL);
+}
+
 static int pool_resize(int workers)
 {
     if (workers == pool.n) return 0;
@@ -438,7 +446,7 @@ static int pool_resize(int workers)
     pool.th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)workers);
     if (!pool.th) return -1;
     static int at_exit_set;
-    if (!at_exit_set) { atexit(pool_shutdown); at_exit_set = 1; }
+    if (!at_exit_set) { atexit(pool_shutdown); pthread_atfork(NULL, NULL, pool_after_fork_child); at_exit_set = 1; }
     for (int t = 0; t < workers; t++)
         if (pthread_create(&pool.th[t], NULL, pool_worker, NULL)) { pool.n = t; pool_shutdown(); return -1; }
     pool.n = workers;
