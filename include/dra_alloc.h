@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DRA_ABI_VERSION      1u
+#define DRA_ABI_VERSION      2u   /* 2: flags on dra_unsuitable_batch, pod mode, sharded global batch, resident mode */
 
 #define DRA_MAX_GPUS_PER_NODE 32u   /* one warp lane per GPU of a node */
 #define DRA_MAX_MODELS        16u
@@ -32,6 +32,8 @@ extern "C" {
 #define DRA_MAX_COUNT         32u   /* devices per GPU claim; k8s caps results per claim at 32
                                        (vendor/k8s.io/api/resource/v1beta1/types.go:792) */
 #define DRA_MAX_GROUP         32u   /* members of one co-location run (same cap) */
+#define DRA_MAX_POD           32u   /* claims of one pod in pod mode (spec §12) */
+#define DRA_EXH_BUDGET        4096u /* descents of the exhaustive placement search per pod evaluation (spec §12) */
 #define DRA_GPU_NONE          0xFFFFFFFFu
 
 /* ---- records (spec/ALLOCATION.md §1) ------------------------------------------------------------ */
@@ -91,6 +93,8 @@ typedef struct dra_out_rec {
 #define DRA_ST_GROUP       3u
 #define DRA_ST_MEM_LIMIT   4u
 #define DRA_ST_INVALID     5u
+#define DRA_ST_POD         6u     /* pod mode (spec §12): the pod does not fit on the node; nothing of it was taken */
+#define DRA_ST_SEARCH_LIMIT 7u    /* pod mode: the exhaustive search ran out of budget (DRA_EXH_BUDGET descents) */
 
 /* One (model, profile) cell of the placement table: what getGpuInfo() collects from
  * GetGpuInstanceProfileInfo + GetGpuInstancePossiblePlacements (nvlib.go:244-295). */
@@ -179,6 +183,11 @@ typedef struct dra_cfg {
 #define DRA_F_FRESH_INVENTORY 0x2u  /* evaluate against the inventory as dra_set_inventory last loaded it
                                    (ignoring earlier batches); the result becomes the live inventory */
 
+#define DRA_F_EXHAUSTIVE 0x4u   /* pod mode (spec §12): backtracking search over every valid (GPU, placement) of the pod's MIG
+                                   claims — a pod fails only if NO assignment exists.  dra_allocate_pods_batch and
+                                   dra_unsuitable_batch; the enumeration it searches is the one deviceLib.getGpuInfo builds
+                                   (cmd/nvidia-dra-plugin/nvlib.go:244-295) */
+
 int  dra_abi_version(void);
 
 /* Creates a context bound to one CUDA device + one stream.  Fails with DRA_E_CUDA when no usable
@@ -233,7 +242,18 @@ int  dra_ctx_sync(dra_ctx* ctx);
 int  dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim,
                           const uint32_t* pod_off, uint32_t n_pod,
                           const uint32_t* cand_nodes, const uint32_t* cand_off,
-                          uint8_t* suitable_bits);
+                          uint8_t* suitable_bits, uint32_t flags /* 0 or DRA_F_EXHAUSTIVE (spec §12) */);
+
+/* Allocate() with pod boundaries (spec §12): what the classic driver's Allocate did after UnsuitableNodes had found
+ * an assignment for ALL of a pod's claims on the selected node — each pod (claims
+ * pod_off[p] .. pod_off[p+1], all naming the same node, at most DRA_MAX_POD) is placed atomically; with
+ * DRA_F_EXHAUSTIVE its MIG claims are placed by the backtracking search over the placement enumeration of
+ * nvlib.go:244-295 (multi-request shape: demo/specs/quickstart/gpu-test4.yaml:19-44).  A pod that does not fit
+ * takes nothing: its slots carry DRA_ST_POD (or DRA_ST_SEARCH_LIMIT).  Host buffers; flags: DRA_F_EXHAUSTIVE,
+ * DRA_F_FRESH_INVENTORY. */
+int  dra_allocate_pods_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim,
+                             const uint32_t* pod_off, uint32_t n_pod,
+                             const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, uint32_t flags);
 
 /* Deallocate(): stands in for controller.Driver.Deallocate(ctx, claim).  Inverse update from the
  * claims and the OutRecs dra_allocate_batch produced for them (same out_off convention). */

@@ -94,6 +94,9 @@ public:
     void SetMigProfiles(uint32_t model, const std::vector<MigProfileInfo>& profiles);
     // replaces the whole inventory (publish / NAS sync)
     void SetNodes(const std::vector<NodeAllocationState>& nodes);
+    // spec §12: evaluate each pod atomically, its MIG claims by the backtracking search over every valid placement
+    // (the classic mig.allocate) instead of in-order first-fit.  Off by default.
+    void SetExhaustive(bool on) { exhaustive_ = on; }
 
     // controller.Driver.Allocate(ctx, claims, selectedNode): mutates the inventory
     void Allocate(const std::vector<ClaimAllocation*>& claims, const std::string& selectedNode);
@@ -128,6 +131,7 @@ private:
     std::vector<uint32_t> gpuLocalIndex_;                       // GpuInfo.index per global gpu
     std::map<uint32_t, std::vector<MigProfileInfo>> profiles_;  // per model
     uint32_t nextGroup_ = 1;
+    bool exhaustive_ = false;
     // what Deallocate needs to undo a claim
     struct Held { std::vector<dra_claim_rec> recs; std::vector<uint32_t> outOff; std::vector<dra_out_rec> out; };
     std::map<std::string, Held> held_;

@@ -16,7 +16,7 @@ SO_PATH = os.path.join(_HERE, "libdra_alloc.so")
 
 OK, E_INVAL, E_CUDA, E_NCCL, E_NOMEM, E_STATE = 0, -1, -2, -3, -4, -5
 CFG_USE_GRAPH, CFG_NO_FUSED, CFG_NO_DIRECT = 0x1, 0x2, 0x4
-F_NODE_SORTED, F_FRESH_INVENTORY = 0x1, 0x2
+F_NODE_SORTED, F_FRESH_INVENTORY, F_EXHAUSTIVE = 0x1, 0x2, 0x4
 
 
 class DraError(RuntimeError):
@@ -46,7 +46,8 @@ SYMBOLS = {
     "dra_allocate_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32]),
     "dra_allocate_batch_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32]),
     "dra_ctx_sync": (_i32, [_vp]),
-    "dra_unsuitable_batch": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _vp]),
+    "dra_unsuitable_batch": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _u32]),
+    "dra_allocate_pods_batch": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _u32]),
     "dra_deallocate_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32]),
     "dra_comm_unique_id": (_i32, [_vp]),
     "dra_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
@@ -89,7 +90,7 @@ def load(build_if_stale: bool = True) -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the ABI and the header drift apart
         fn.restype, fn.argtypes = res, args
-    if lib.dra_abi_version() != 1:
+    if lib.dra_abi_version() != 2:
         raise RuntimeError("libdra_alloc ABI version mismatch")
     _lib = lib
     return lib
@@ -134,7 +135,7 @@ class Context:
 
     def __init__(self, device: int = 0, stream: int | None = None, max_claims: int = 0, flags: int = 0):
         self._lib = load()
-        cfg = _Cfg(1, device, C.c_void_p(stream) if stream else None, max_claims, flags)
+        cfg = _Cfg(2, device, C.c_void_p(stream) if stream else None, max_claims, flags)
         h = C.c_void_p()
         rc = self._lib.dra_ctx_create(C.byref(cfg), C.byref(h))
         if rc != OK:
@@ -237,21 +238,34 @@ class Context:
                                                                _ptr(d_out_off), _ptr(d_out_all), n_out,
                                                                n_per_rank, flags))
 
-    def unsuitable(self, claims, pod_off, cand_nodes=None, cand_off=None) -> np.ndarray:
-        """cand_nodes/cand_off None = dense form: every pod against every node (bit k = pod * n_node + node)."""
+    def allocate_pods(self, claims, pod_off, out_off=None, n_out=None, flags: int = 0) -> np.ndarray:
+        """Pod mode (spec §12): every pod atomically; flags & F_EXHAUSTIVE = backtracking placement search."""
+        c = np.ascontiguousarray(claims, dtype=R.CLAIM_DTYPE)
+        po = np.ascontiguousarray(pod_off, dtype=np.uint32)
+        oo = None if out_off is None else np.ascontiguousarray(out_off, dtype=np.uint32)
+        if n_out is None:
+            n_out = len(c) if oo is None else int(R.claim_slots(c, self.n_node).sum())
+        out = np.zeros(n_out, dtype=R.OUT_DTYPE)
+        self._check(self._lib.dra_allocate_pods_batch(self._h, _ptr(c), len(c), _ptr(po), len(po) - 1, _ptr(oo), _ptr(out),
+                                                      n_out, flags))
+        return out
+
+    def unsuitable(self, claims, pod_off, cand_nodes=None, cand_off=None, flags: int = 0) -> np.ndarray:
+        """cand_nodes/cand_off None = dense form: every pod against every node (bit k = pod * n_node + node).
+        flags & F_EXHAUSTIVE: spec §12 — unsuitable only if NO assignment of the pod exists."""
         c = np.ascontiguousarray(claims, dtype=R.CLAIM_DTYPE)
         po = np.ascontiguousarray(pod_off, dtype=np.uint32)
         if cand_nodes is None:
             n_pair = (len(po) - 1) * self.n_node
             bits = np.zeros((n_pair + 7) // 8 + 8, dtype=np.uint8)
-            self._check(self._lib.dra_unsuitable_batch(self._h, _ptr(c), len(c), _ptr(po), len(po) - 1, None, None, _ptr(bits)))
+            self._check(self._lib.dra_unsuitable_batch(self._h, _ptr(c), len(c), _ptr(po), len(po) - 1, None, None, _ptr(bits), flags))
             return bits[: (n_pair + 7) // 8]
         cn = np.ascontiguousarray(cand_nodes, dtype=np.uint32)
         co = np.ascontiguousarray(cand_off, dtype=np.uint32)
         n_pair = int(co[-1])
         bits = np.zeros((n_pair + 7) // 8 + 8, dtype=np.uint8)
         self._check(self._lib.dra_unsuitable_batch(self._h, _ptr(c), len(c), _ptr(po), len(po) - 1,
-                                                   _ptr(cn), _ptr(co), _ptr(bits)))
+                                                   _ptr(cn), _ptr(co), _ptr(bits), flags))
         return bits[: (n_pair + 7) // 8]
 
     def deallocate(self, claims, out, out_off=None):

@@ -90,6 +90,7 @@ struct dra_ctx {
     uint32_t* d_hist = nullptr;
     uint32_t* d_claim_off = nullptr;
     uint32_t *d_pod_off = nullptr, *d_cand_off = nullptr, *d_cand_nodes = nullptr, *d_pair_pod = nullptr, *d_bits = nullptr;
+    uint4* d_podrec = nullptr; size_t cap_podrec = 0;     // pod mode (spec §12)
 
     // error flags
     uint32_t* d_err = nullptr;            // device memory
@@ -265,10 +266,79 @@ FusedPlan fused_plan(const dra_ctx* ctx, uint32_t n_claim, uint32_t flags) {
     // Measured crossover against the sort path (profiles/path_crossover_r01f.txt): the single launch costs about
     // 4 us + 1.2 us per 1000 claims while all CTAs fit one wave (10 us + 1.4 us beyond), the sort path about
     // 20 us + 0.2 us per 1000 claims.
-    const uint32_t fused_max_claims = n_node + 1 <= 148 ? 14000u : 7500u;
+    const uint32_t fused_max_claims = (int)(n_node + 1) <= ctx->n_sm ? 14000u : 7500u;   // one wave of CTAs or not
     p.fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) && n_claim <= fused_max_claims &&
               (uint64_t)n_node * n_claim <= ctx->fused_max_work && p.smem <= 225 * 1024 && n_node <= 16384;
     return p;
+}
+
+// Stable counting sort of 16-byte records by their node key (.y) into ctx->d_sorted + ctx->d_claim_off — the
+// front half of the sort path.  Records naming no node get an INVALID OutRec (d_out != nullptr) or are dropped
+// (d_out == nullptr: pod records).  Enqueues only.
+int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off, uint2* d_out,
+                uint32_t n_out, uint32_t flags, Prof& prof, const void* inv_src, bool pdl) {
+    const uint32_t n_node = ctx->n_node;
+    Err err = err_of(ctx);
+    // sort path: the kernels after the first are programmatic dependents of their predecessor (launch latency and
+    // prologue overlap the predecessor's tail); not while per-kernel events are being recorded
+    if (flags & DRA_F_NODE_SORTED) {
+        uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
+        k_sorted_prep<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
+                                                       ctx->d_sorted, d_out, n_out, err);
+        ctx->launches += 1;
+        prof.mark(); prof.skip_to(3);
+    } else {
+        const size_t nbp = ((size_t)n_node + 2) & ~(size_t)1;
+        const size_t small_smem = nbp * 4 + 32 * nbp * 2 + (size_t)n_claim * 2 + 16;
+        if (n_claim <= 8192 && small_smem <= 200 * 1024) {
+            // one launch: the whole stable counting sort in a single CTA
+            if (small_smem > 48 * 1024 && ctx->small_smem_set < (int)small_smem) {
+                CU(cudaFuncSetAttribute(k_bucket_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+                ctx->small_smem_set = (int)small_smem;
+            }
+            Prefetch pf;
+            pf.p[0] = inv_src;
+            pf.bytes[0] = std::min<uint32_t>(ctx->n_gpu * 16u, 1u << 20) & ~15u;
+            pf.p[1] = ctx->d_node_off; pf.bytes[1] = std::min<uint32_t>((n_node + 1) * 4u, 1u << 20) & ~15u;
+            pf.p[2] = ctx->d_tbl; pf.bytes[2] = 1024;
+            k_bucket_small<<<1, 1024, small_smem, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
+                                                                 ctx->d_sorted, d_out, n_out, err, pf);
+            ctx->launches += 1;
+            prof.mark(); prof.skip_to(3);
+        } else {
+            Tiling t = tiling(n_claim, n_node);
+            if (t.cta_wide) {
+                const size_t smem = (size_t)8 * (((size_t)n_node + 2) & ~(size_t)1) * 2;
+                if (smem > 48 * 1024 && ctx->hist8_smem_set < (int)smem) {
+                    CU(cudaFuncSetAttribute(k_bucket_hist8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ctx->hist8_smem_set = (int)smem;
+                }
+                if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
+                k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank);
+                prof.mark();
+                CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 7) / 8), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
+                prof.mark();
+            } else {
+                size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
+                if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
+                if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
+                    CU(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ctx->hist_smem_set = (int)smem;
+                }
+                k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
+                prof.mark();
+                CU(launch_k(k_bucket_scan, dim3(1), dim3(1024), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off));
+                prof.mark();
+            }
+            uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
+            CU(launch_k(k_bucket_scatter, dim3(blocks), dim3(256), 0, ctx->stream, pdl, d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
+                        ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err));
+            prof.mark();
+            ctx->launches += 3;
+        }
+    }
+
+    return DRA_OK;
 }
 
 int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
@@ -352,72 +422,15 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         return DRA_OK;
     }
 
-    // sort path: the kernels after the first are programmatic dependents of their predecessor (launch latency and
-    // prologue overlap the predecessor's tail); not while per-kernel events are being recorded
     static const bool no_pdl = getenv("DRA_NO_PDL") != nullptr;
     const bool pdl = !no_pdl && !ctx->profiling;
-    if (flags & DRA_F_NODE_SORTED) {
-        uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
-        k_sorted_prep<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
-                                                       ctx->d_sorted, d_out, n_out, err);
-        ctx->launches += 1;
-        prof.mark(); prof.skip_to(3);
-    } else {
-        const size_t nbp = ((size_t)n_node + 2) & ~(size_t)1;
-        const size_t small_smem = nbp * 4 + 32 * nbp * 2 + (size_t)n_claim * 2 + 16;
-        if (n_claim <= 8192 && small_smem <= 200 * 1024) {
-            // one launch: the whole stable counting sort in a single CTA
-            if (small_smem > 48 * 1024 && ctx->small_smem_set < (int)small_smem) {
-                CU(cudaFuncSetAttribute(k_bucket_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
-                ctx->small_smem_set = (int)small_smem;
-            }
-            Prefetch pf;
-            pf.p[0] = a.inv_src;
-            pf.bytes[0] = std::min<uint32_t>(ctx->n_gpu * 16u, 1u << 20) & ~15u;
-            pf.p[1] = ctx->d_node_off; pf.bytes[1] = std::min<uint32_t>((n_node + 1) * 4u, 1u << 20) & ~15u;
-            pf.p[2] = ctx->d_tbl; pf.bytes[2] = 1024;
-            k_bucket_small<<<1, 1024, small_smem, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
-                                                                 ctx->d_sorted, d_out, n_out, err, pf);
-            ctx->launches += 1;
-            prof.mark(); prof.skip_to(3);
-        } else {
-            Tiling t = tiling(n_claim, n_node);
-            if (t.cta_wide) {
-                const size_t smem = (size_t)8 * (((size_t)n_node + 2) & ~(size_t)1) * 2;
-                if (smem > 48 * 1024 && ctx->hist8_smem_set < (int)smem) {
-                    CU(cudaFuncSetAttribute(k_bucket_hist8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    ctx->hist8_smem_set = (int)smem;
-                }
-                if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
-                k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank);
-                prof.mark();
-                CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 7) / 8), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
-                prof.mark();
-            } else {
-                size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
-                if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
-                if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
-                    CU(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    ctx->hist_smem_set = (int)smem;
-                }
-                k_bucket_hist<<<t.n_tiles, 32, smem, ctx->stream>>>(d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank);
-                prof.mark();
-                CU(launch_k(k_bucket_scan, dim3(1), dim3(1024), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off));
-                prof.mark();
-            }
-            uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
-            CU(launch_k(k_bucket_scatter, dim3(blocks), dim3(256), 0, ctx->stream, pdl, d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
-                        ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err));
-            prof.mark();
-            ctx->launches += 3;
-        }
-    }
+    if ((rc = launch_sort(ctx, d_claims, n_claim, d_out_off, d_out, n_out, flags, prof, a.inv_src, pdl))) return rc;
 
     a.sorted = ctx->d_sorted;
     a.claim_off = ctx->d_claim_off;
     if (n_node) {
-        if (n_node <= 148u * 16u) CU(launch_k(k_pack<1>, dim3(n_node), dim3(32), pack_smem_bytes(1), ctx->stream, pdl, a));
-        else CU(launch_k(k_pack<4>, dim3(std::min((n_node + 3) / 4, 148u * 8u)), dim3(128), pack_smem_bytes(4), ctx->stream, pdl, a));
+        if (n_node <= (uint32_t)ctx->n_sm * 16u) CU(launch_k(k_pack<1>, dim3(n_node), dim3(32), pack_smem_bytes(1), ctx->stream, pdl, a));
+        else CU(launch_k(k_pack<4>, dim3(std::min((n_node + 3) / 4, (uint32_t)ctx->n_sm * 8u)), dim3(128), pack_smem_bytes(4), ctx->stream, pdl, a));
         ctx->launches += 1;
     }
     prof.mark();
@@ -512,7 +525,7 @@ void dra_ctx_destroy(dra_ctx* c) {
     if (c->d_gbar) cudaFree(c->d_gbar);
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
-                   c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels};
+                   c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels, c->d_podrec};
     for (void* p : dev) if (p) cudaFree(p);
     if (c->h_err) cudaFreeHost((void*)c->h_err);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -584,6 +597,7 @@ int dra_set_gpu_attrs(dra_ctx* ctx, const dra_gpu_attr* attrs, uint32_t n_gpu) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_attrs) { CU(cudaFree(ctx->d_attrs)); ctx->d_attrs = nullptr; }
     ctx->n_attr = 0;
+    ctx->state_epoch++;                      // a captured graph holds the freed pointer: never replay it
     if (!n_gpu) return DRA_OK;
     CU(cudaMalloc((void**)&ctx->d_attrs, (size_t)n_gpu * 16 + 64));
     CU(cudaMemcpy(ctx->d_attrs, attrs, (size_t)n_gpu * 16, cudaMemcpyHostToDevice));
@@ -598,6 +612,7 @@ int dra_set_selectors(dra_ctx* ctx, const dra_selector* sels, uint32_t n_sel) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_sels) { CU(cudaFree(ctx->d_sels)); ctx->d_sels = nullptr; }
     ctx->n_sel = 0;
+    ctx->state_epoch++;
     if (!n_sel) return DRA_OK;
     CU(cudaMalloc((void**)&ctx->d_sels, (size_t)n_sel * 64 + 64));
     CU(cudaMemcpy(ctx->d_sels, sels, (size_t)n_sel * 64, cudaMemcpyHostToDevice));
@@ -753,12 +768,14 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
 }
 
 int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* pod_off, uint32_t n_pod,
-                         const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits) {
+                         const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits, uint32_t flags) {
     if (!ctx || !pod_off || (n_claim && !claims)) return DRA_E_INVAL;
+    if (flags & ~DRA_F_EXHAUSTIVE) return fail(ctx, DRA_E_INVAL, "dra_unsuitable_batch: unknown flags 0x%x", flags);
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
-    if (pod_off[n_pod] != n_claim) return fail(ctx, DRA_E_INVAL, "pod_off[n_pod] != n_claim");
+    if (pod_off[0] != 0 || pod_off[n_pod] != n_claim) return fail(ctx, DRA_E_INVAL, "pod_off must span [0, n_claim]");
     const bool dense = cand_nodes == nullptr && cand_off == nullptr;      // every pod against every node
     if (!dense && !cand_off) return DRA_E_INVAL;
+    if (!dense && cand_off[0] != 0) return fail(ctx, DRA_E_INVAL, "cand_off[0] must be 0");
     const uint64_t n_pair64 = dense ? (uint64_t)n_pod * ctx->n_node : cand_off[n_pod];
     if (n_pair64 > 0xFFFFFFF0ull) return fail(ctx, DRA_E_INVAL, "too many (pod, node) pairs");
     const uint32_t n_pair = (uint32_t)n_pair64;
@@ -819,11 +836,12 @@ int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
         a.inv = ctx->d_inv_live; a.node_off = ctx->d_node_off; a.n_node = ctx->n_node; a.tbl = ctx->d_tbl; a.bits = ctx->d_bits;
         a.sel = sel_of(ctx);
         a.dense = dense ? 1u : 0u;
+        a.exhaustive = (flags & DRA_F_EXHAUSTIVE) ? 1u : 0u;
         Prof prof(ctx);
         // lanes per pair from the widest node: 8 lanes = 4 pairs per warp
         const uint32_t W = ctx->max_width <= 8 ? 8u : (ctx->max_width <= 16 ? 16u : 32u);
         const uint32_t per_cta = 8 * (32 / W);
-        const uint32_t grid = std::max(1u, std::min((n_pair + per_cta - 1) / per_cta, 148u * 8u));
+        const uint32_t grid = std::max(1u, std::min((n_pair + per_cta - 1) / per_cta, (uint32_t)ctx->n_sm * 8u));
         if (W == 8) k_unsuitable<8, 8><<<grid, 256, 0, ctx->stream>>>(a);
         else if (W == 16) k_unsuitable<8, 16><<<grid, 256, 0, ctx->stream>>>(a);
         else k_unsuitable<8, 32><<<grid, 256, 0, ctx->stream>>>(a);
@@ -837,6 +855,71 @@ int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
     if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "k_unsuitable: %s", cudaGetErrorString(e));
     collect_timings(ctx, 1);
     if (n_pair) memcpy(suitable_bits, ctx->h_out, ((size_t)n_pair + 7) / 8);
+    return DRA_OK;
+}
+
+// Allocate with pod boundaries (spec §12): pod records -> stable counting sort of the PODS by node (the claim path's
+// bucketing kernels, the record has a ClaimRec's layout) -> one warp per node walks its pods in input order.
+int dra_allocate_pods_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* pod_off, uint32_t n_pod,
+                            const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, uint32_t flags) {
+    if (!ctx || !pod_off || (n_claim && (!claims || !out))) return DRA_E_INVAL;
+    if (flags & ~(DRA_F_EXHAUSTIVE | DRA_F_FRESH_INVENTORY)) return fail(ctx, DRA_E_INVAL, "dra_allocate_pods_batch: unknown flags 0x%x", flags);
+    if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
+    if (pod_off[0] != 0 || pod_off[n_pod] != n_claim) return fail(ctx, DRA_E_INVAL, "pod_off must span [0, n_claim]");
+    if (!out_off && n_out < n_claim) return fail(ctx, DRA_E_INVAL, "n_out %u < n_claim %u without out_off", n_out, n_claim);
+    for (uint32_t q = 0; q < n_pod; ++q)
+        if (pod_off[q + 1] < pod_off[q]) return fail(ctx, DRA_E_INVAL, "pod_off not monotone at pod %u", q);
+    if (!n_pod) return DRA_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_batch(ctx, std::max(n_claim, n_pod), n_out, true);
+    if (rc) return rc;
+    if ((rc = upload_table(ctx))) return rc;
+    if (n_pod + 8 > ctx->cap_pods) {
+        size_t cap = (size_t)n_pod + n_pod / 2 + 64;
+        if ((rc = grow_nc(ctx, ctx->d_pod_off, 0, cap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_cand_off, 0, cap))) return rc;
+        ctx->cap_pods = cap;
+    }
+    if (n_pod + 8 > ctx->cap_podrec) {
+        size_t cap = (size_t)n_pod + n_pod / 2 + 64;
+        if ((rc = grow_nc(ctx, ctx->d_podrec, 0, cap))) return rc;
+        ctx->cap_podrec = cap;
+    }
+    const size_t cb = (size_t)n_claim * 16, pb = ((size_t)n_pod + 1) * 4, ob = out_off ? (size_t)n_claim * 4 : 0, rb = (size_t)n_out * 8;
+    if ((rc = grow_pinned(ctx, ctx->h_in, ctx->h_in_cap, cb + pb + ob))) return rc;
+    if ((rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, rb + 16))) return rc;
+    if (cb) memcpy(ctx->h_in, claims, cb);
+    memcpy(ctx->h_in + cb, pod_off, pb);
+    if (ob) memcpy(ctx->h_in + cb + pb, out_off, ob);
+    if (cb) CU(cudaMemcpyAsync(ctx->d_claims, ctx->h_in, cb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pod_off, ctx->h_in + cb, pb, cudaMemcpyHostToDevice, ctx->stream));
+    if (ob) CU(cudaMemcpyAsync(ctx->d_out_off, ctx->h_in + cb + pb, ob, cudaMemcpyHostToDevice, ctx->stream));
+    Err err = err_of(ctx);
+    Prof prof(ctx);
+    uint2* d_out = ctx->d_out;
+    const uint32_t* d_oo = out_off ? ctx->d_out_off : nullptr;
+    k_pod_records<<<(n_pod + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_claims, ctx->d_pod_off, n_pod, ctx->n_node, d_oo, d_out, n_out, ctx->d_podrec, err);
+    ctx->launches += 1;
+    static const bool no_pdl = getenv("DRA_NO_PDL") != nullptr;
+    const bool pdl = !no_pdl && !ctx->profiling;
+    const uint4* inv_src = (flags & DRA_F_FRESH_INVENTORY) ? ctx->d_inv_pristine : ctx->d_inv_live;
+    if ((rc = launch_sort(ctx, ctx->d_podrec, n_pod, nullptr, nullptr, 0, 0, prof, inv_src, false))) return rc;
+    PodArgs a; memset(&a, 0, sizeof a);
+    a.claims = ctx->d_claims; a.out_off = d_oo; a.out = d_out;
+    a.sorted = ctx->d_sorted; a.claim_off = ctx->d_claim_off;
+    a.inv_src = inv_src; a.inv_dst = ctx->d_inv_live; a.node_off = ctx->d_node_off; a.tbl = ctx->d_tbl;
+    a.n_node = ctx->n_node; a.exhaustive = (flags & DRA_F_EXHAUSTIVE) ? 1u : 0u; a.sel = sel_of(ctx); a.err = err;
+    if (ctx->n_node) {
+        const uint32_t grid = std::max(1u, std::min((ctx->n_node + 3) / 4, (uint32_t)ctx->n_sm * 8u));
+        CU(launch_k(k_pods<4>, dim3(grid), dim3(128), 0, ctx->stream, pdl, a));
+        ctx->launches += 1;
+    }
+    if (rb) CU(cudaMemcpyAsync(ctx->h_out, d_out, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "pod kernels: %s", cudaGetErrorString(e));
+    if ((rc = check_err(ctx))) return rc;
+    if (rb) memcpy(out, ctx->h_out, rb);
     return DRA_OK;
 }
 

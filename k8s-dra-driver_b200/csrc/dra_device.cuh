@@ -597,6 +597,7 @@ k_bucket_scatter(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_
         const uint32_t kind = c.x & 0xFFu;
         const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU
                           : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
+        if (!out) return;                                  // pod records (k_pod_records has reported them)
         if (dst < n_out) out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
         else err.set(ERR_OUT_RANGE);
         return;
@@ -727,6 +728,7 @@ k_bucket_small(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_no
                 const uint32_t kind = c.x & 0xFFu;
                 const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU
                                   : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
+                if (!out) continue;                        // pod records
                 if (dst < n_out) out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
                 else err.set(ERR_OUT_RANGE);
                 continue;
@@ -1592,6 +1594,234 @@ k_fused(const PackArgs a) {
 }
 
 // ====================================================================================================
+// pod mode (spec §12): atomic evaluation of a pod on one node, with the exhaustive placement search
+// ====================================================================================================
+// What is searched is the (profile, placement) enumeration deviceLib.getGpuInfo builds per GPU
+// (cmd/nvidia-dra-plugin/nvlib.go:244-295, here: the placement table); the multi-request shape is
+// demo/specs/quickstart/gpu-test4.yaml:19-44.  The classic driver's recursive search tried one candidate after
+// another; here one lane holds one GPU of the node, a level's candidates on ALL GPUs are computed at
+// once (shift/AND fit map per lane), a ballot picks the canonical next one (lowest GPU, lowest start), and the
+// search stack is two registers per lane: the levels at which this lane's GPU was chosen and the start it got.
+
+// sink of the non-MIG claims of a pod: records go straight to out (rewritten with POD if the pod fails later)
+struct PodSink {
+    uint2* out; bool failed = false;
+    __device__ __forceinline__ bool range(uint32_t, uint32_t) const { return true; }     // checked by k_pod_records
+    __device__ __forceinline__ void put(uint32_t idx, uint32_t gpu, uint32_t m) const { if (out) out[idx] = make_uint2(gpu, m); }
+    __device__ __forceinline__ bool in_range(uint32_t) const { return true; }
+    __device__ __forceinline__ void fail(uint32_t, uint32_t, uint32_t, uint32_t) { failed = true; }
+    __device__ __forceinline__ void mark_failed() { failed = true; }
+    __device__ __forceinline__ bool stop() const { return failed; }
+};
+
+struct PodGet {            // claim m of the pod, .y = its first OutRec slot
+    const uint4* pc; const uint32_t* slot; uint32_t base;
+    __device__ __forceinline__ uint4 operator()(uint32_t m) const {
+        uint4 c = __ldg(&pc[m]);
+        c.y = slot ? __ldg(&slot[m]) : base + m;
+        return c;
+    }
+};
+
+// Evaluates the pod pc[0..cnt) (cnt <= 32) on the node whose GPUs sit on the W lanes gbase.. of this warp.
+// Returns 0 when the pod was placed (L updated, OutRecs written when out != nullptr), else the failure status
+// (L untouched, every slot of the pod rewritten with it / INVALID).  All lanes of the group must call it together.
+template <int W>
+__device__ __noinline__ uint32_t pod_eval(Lane& L, const uint32_t lane, const uint32_t gmask, const uint32_t gbase,
+                                          const uint32_t g0, const uint32_t* __restrict__ tbl_s, const PodGet get,
+                                          const uint32_t cnt, const SelCtx sc, const bool exhaustive, const bool have_off,
+                                          uint2* __restrict__ out) {
+    constexpr uint32_t BLOCKED = DRA_GPU_MIG_ENABLED | DRA_GPU_FULL_ALLOCATED | DRA_GPU_UNAVAILABLE;
+    constexpr int R = 32 / W;
+    const uint32_t gl = lane - gbase;
+    const Lane L0 = L;
+    // ---- 1. classify, lane-parallel: lane gl looks at claims gl, gl+W, ... ----
+    uint32_t invmask = 0, migmask = 0, grpmask = 0;
+    #pragma unroll
+    for (int q = 0; q < R; ++q) {
+        const uint32_t idx = q * W + gl;
+        const bool present = idx < cnt;
+        uint4 c = make_uint4(0, 0, 0, 0);
+        if (present) c = get(idx);
+        const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
+        const bool inv = present && (claim_invalid(kind, prof, count, have_off) || claim_sel(kind, c.z, c.w) > sc.n_sel);
+        const bool mig = present && kind == DRA_KIND_MIG;
+        invmask |= ((__ballot_sync(gmask, inv) & gmask) >> gbase) << (q * W);
+        migmask |= ((__ballot_sync(gmask, mig) & gmask) >> gbase) << (q * W);
+        grpmask |= ((__ballot_sync(gmask, mig && c.w != 0) & gmask) >> gbase) << (q * W);
+    }
+    uint32_t status = invmask ? (uint32_t)DRA_ST_POD : 0u;
+    // ---- 2. the GPU / SHARED claims, in order, by the default rules (spec §4, §7) ----
+    if (!status) {
+        PodSink ps{out};
+        Dead D;
+        uint32_t nm = (cnt >= 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) & ~migmask;
+        while (nm && !ps.failed) {
+            const uint32_t pos = (uint32_t)__ffs(nm) - 1u; nm &= nm - 1u;
+            (void)node_step(L, D, lane, g0, tbl_s, get, pos, cnt, ps, have_off, sc, gmask, gbase);
+        }
+        if (ps.failed) status = DRA_ST_POD;
+    }
+    // ---- 3. the MIG claims: depth-first search in canonical order (GPUs ascending, starts ascending) ----
+    uint32_t chosen = 0;                       // bit pos: this lane's GPU holds the claim at position pos
+    unsigned long long st_lo = 0, st_hi = 0;   // its start there, one nibble per position
+    if (!status && migmask) {
+        uint32_t descents = 0, pos = (uint32_t)__ffs(migmask) - 1u;
+        uint32_t rl = 0xFFFFFFFFu, rs = 0;     // resume point after a backtrack: candidates after (lane rl, start rs)
+        while (true) {
+            const uint4 c = get(pos);
+            const uint32_t prof = (c.x >> 8) & 0xFFu, group = c.w;
+            const uint32_t e = tbl_s[L.model * DRA_MAX_PROFILES + prof];
+            const uint32_t smask = e >> 16, size = e & 0xFFu;
+            bool ok = L.valid && (L.flags & BLOCKED) == DRA_GPU_MIG_ENABLED && smask != 0;
+            if (c.z != 0) ok = sel_pass(sc, c.z, g0 + gl, L.valid) && ok;
+            if (group != 0 && (grpmask & ((1u << pos) - 1u))) {                  // co-location: the first earlier member's GPU
+                uint32_t be = grpmask & ((1u << pos) - 1u);
+                while (be) {
+                    const uint32_t j = (uint32_t)__ffs(be) - 1u; be &= be - 1u;
+                    if (get(j).w == group) { ok = ok && ((chosen >> j) & 1u); break; }
+                }
+            }
+            uint32_t cand = ok ? (fit_map(~L.busy & 0xFFFFu, size) & smask) : 0u;
+            if (rl != 0xFFFFFFFFu) { if (gl < rl) cand = 0; else if (gl == rl) cand &= ~((2u << rs) - 1u); }
+            const uint32_t b = __ballot_sync(gmask, cand != 0) & gmask;
+            if (b) {
+                if (descents == DRA_EXH_BUDGET) { status = DRA_ST_SEARCH_LIMIT; break; }
+                ++descents;
+                if (lane == (uint32_t)__ffs(b) - 1u) {
+                    const uint32_t s_ = (uint32_t)__ffs(cand) - 1u;
+                    L.busy |= ((1u << size) - 1u) << s_;
+                    chosen |= 1u << pos;
+                    if (pos < 16u) st_lo = (st_lo & ~(0xFull << (4u * pos))) | ((unsigned long long)s_ << (4u * pos));
+                    else st_hi = (st_hi & ~(0xFull << (4u * (pos - 16u)))) | ((unsigned long long)s_ << (4u * (pos - 16u)));
+                }
+                const uint32_t rem = pos >= 31u ? 0u : (migmask & ~((2u << pos) - 1u));
+                if (!rem) break;                                                  // every level placed
+                pos = (uint32_t)__ffs(rem) - 1u; rl = 0xFFFFFFFFu;
+            } else {
+                const uint32_t below = migmask & ((1u << pos) - 1u);
+                if (!exhaustive || !below) { status = DRA_ST_POD; break; }
+                pos = 31u - (uint32_t)__clz(below);                               // back to the previous level: undo it
+                const uint32_t p2 = (get(pos).x >> 8) & 0xFFu;
+                const uint32_t size2 = tbl_s[L.model * DRA_MAX_PROFILES + p2] & 0xFFu;
+                const bool mine = (chosen >> pos) & 1u;
+                const uint32_t s2 = (uint32_t)((pos < 16u ? st_lo >> (4u * pos) : st_hi >> (4u * (pos - 16u))) & 0xFull);
+                const uint32_t wl = __ballot_sync(gmask, mine) & gmask;
+                const uint32_t wabs = (uint32_t)__ffs(wl) - 1u;
+                if (mine) { L.busy &= ~(((1u << size2) - 1u) << s2); chosen &= ~(1u << pos); }
+                rs = __shfl_sync(gmask, s2, wabs);
+                rl = wabs - gbase;
+            }
+        }
+    }
+    __syncwarp(gmask);
+    if (status) {
+        L = L0;
+        if (out) {                                          // every slot of the pod: INVALID for the malformed claims, else POD / LIMIT
+            #pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const uint32_t idx = q * W + gl;
+                if (idx >= cnt) continue;
+                const uint4 c = get(idx);
+                const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
+                const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : prof;
+                const uint32_t slots = (kind == DRA_KIND_GPU && !claim_invalid(kind, prof, count, have_off)) ? count : 1u;
+                const uint32_t st = ((invmask >> idx) & 1u) ? (uint32_t)DRA_ST_INVALID : status;
+                for (uint32_t k = 0; k < slots; ++k) out[c.y + k] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, st));
+            }
+        }
+        return status;
+    }
+    if (out) {
+        uint32_t m = chosen;
+        while (m) {
+            const uint32_t pos = (uint32_t)__ffs(m) - 1u; m &= m - 1u;
+            const uint4 c = get(pos);
+            const uint32_t prof = (c.x >> 8) & 0xFFu;
+            const uint32_t size = tbl_s[L.model * DRA_MAX_PROFILES + prof] & 0xFFu;
+            const uint32_t s_ = (uint32_t)((pos < 16u ? st_lo >> (4u * pos) : st_hi >> (4u * (pos - 16u))) & 0xFull);
+            out[c.y] = make_uint2(g0 + gl, meta(s_, size, prof, DRA_ST_OK));
+        }
+    }
+    return 0;
+}
+
+// thread per pod: validates the pod (spec §12: <= 32 claims, one node, slots inside out[]) and writes its record
+//   {x = claims in the pod, y = node (0xFFFFFFFF: nothing to evaluate), z = first claim, w = 0}
+// in the layout of a ClaimRec, so that the stable counting sort by node of the claim path orders the PODS by node.
+// Malformed pods get their INVALID records here.
+__global__ void __launch_bounds__(256)
+k_pod_records(const uint4* __restrict__ claims, const uint32_t* __restrict__ pod_off, uint32_t n_pod, uint32_t n_node,
+              const uint32_t* __restrict__ out_off, uint2* __restrict__ out, uint32_t n_out, uint4* __restrict__ podrec, Err err) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pod) return;
+    const uint32_t c0 = __ldg(&pod_off[p]), c1 = __ldg(&pod_off[p + 1]);
+    const uint32_t n = c1 - c0;
+    uint4 rec = make_uint4(n, 0xFFFFFFFFu, c0, 0);
+    if (n == 0 || c1 < c0) { podrec[p] = rec; return; }
+    const bool have_off = out_off != nullptr;
+    const uint32_t node = __ldg(&claims[c0]).y;
+    bool bad = n > DRA_MAX_POD || node >= n_node, oor = false;
+    for (uint32_t i = c0; i < c1; ++i) {
+        const uint4 c = __ldg(&claims[i]);
+        const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
+        bad = bad || c.y != node;
+        const uint32_t slots = (kind == DRA_KIND_GPU && c.y < n_node && !claim_invalid(kind, prof, count, have_off)) ? count : 1u;
+        const uint32_t dst = have_off ? __ldg(&out_off[i]) : i;
+        oor = oor || dst > n_out || slots > n_out - dst;
+    }
+    if (oor) { err.set(ERR_OUT_RANGE); podrec[p] = rec; return; }
+    if (bad) {
+        for (uint32_t i = c0; i < c1; ++i) {
+            const uint4 c = __ldg(&claims[i]);
+            const uint32_t kind = c.x & 0xFFu, prof = (c.x >> 8) & 0xFFu, count = c.x >> 16;
+            const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : prof;
+            const uint32_t slots = (kind == DRA_KIND_GPU && c.y < n_node && !claim_invalid(kind, prof, count, have_off)) ? count : 1u;
+            const uint32_t dst = have_off ? __ldg(&out_off[i]) : i;
+            for (uint32_t k = 0; k < slots; ++k) out[dst + k] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+        }
+        podrec[p] = rec; return;
+    }
+    rec.y = node;
+    podrec[p] = rec;
+}
+
+struct PodArgs {
+    const uint4* claims; const uint32_t* out_off; uint2* out;
+    const uint4* sorted;          // pod records grouped by node (stable), output of the bucketing kernels
+    const uint32_t* claim_off;    // [n_node+2] offsets into sorted
+    const uint4* inv_src; uint4* inv_dst; const uint32_t* node_off; const uint32_t* tbl;
+    uint32_t n_node, exhaustive; SelCtx sel; Err err;
+};
+
+// one warp per node, one lane per GPU; the node's pods in input order
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32)
+k_pods(const PodArgs a) {
+    __shared__ uint32_t tbl_s[DRA_MAX_MODELS * DRA_MAX_PROFILES];
+    pdl_wait();
+    for (uint32_t i = threadIdx.x; i < DRA_MAX_MODELS * DRA_MAX_PROFILES; i += WPC * 32) tbl_s[i] = __ldg(&a.tbl[i]);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t node = blockIdx.x * WPC + wid; node < a.n_node; node += gridDim.x * WPC) {
+        const uint32_t g0 = __ldg(&a.node_off[node]), ng = __ldg(&a.node_off[node + 1]) - g0;
+        const uint32_t p0 = __ldcg(&a.claim_off[node]), p1 = __ldcg(&a.claim_off[node + 1]);
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (lane < ng) rec = __ldg(&a.inv_src[g0 + lane]);
+        Lane L; L.load(rec, lane < ng);
+        for (uint32_t m = p0; m < p1; ++m) {
+            const uint4 pr = __ldcg(&a.sorted[m]);
+            const PodGet get{a.claims + pr.z, a.out_off ? a.out_off + pr.z : nullptr, pr.z};
+            Lane Lt = L;
+            (void)pod_eval<32>(Lt, lane, FULLMASK, 0, g0, tbl_s, get, pr.x, a.sel, a.exhaustive != 0, a.out_off != nullptr, a.out);
+            L = Lt;
+            __syncwarp();
+        }
+        if (lane < ng && (p1 > p0 || a.inv_src != a.inv_dst)) a.inv_dst[g0 + lane] = L.store(rec);
+    }
+}
+
+// ====================================================================================================
 // UnsuitableNodes: warp per (pod, candidate) pair on a snapshot
 // ====================================================================================================
 
@@ -1603,6 +1833,7 @@ struct UnsArgs {
     uint32_t* bits;     // n_pair bits, zeroed by the caller, set with atomicOr
     SelCtx sel;
     uint32_t dense;     // 1: every pod x every node, pair = pod * n_node + node (cand arrays unused)
+    uint32_t exhaustive; // spec §12: pod evaluation with the backtracking search
 };
 
 struct GlobalGet {
@@ -1630,7 +1861,7 @@ k_unsuitable(const UnsArgs a) {
         uint32_t pod, node;
         if (a.dense) { pod = pair / a.n_node; node = pair - pod * a.n_node; }
         else { pod = __ldg(&a.pair_pod[pair]); node = __ldg(&a.cand_nodes[pair]); }
-        if (node >= a.n_node) continue;                                   // unknown node: unsuitable
+        if (node >= a.n_node || pod >= a.n_pod) continue;                 // unknown node: unsuitable
         const uint32_t c0 = __ldg(&a.pod_off[pod]);
         const uint32_t cnt = __ldg(&a.pod_off[pod + 1]) - c0;
         const uint32_t g0 = __ldg(&a.node_off[node]);
@@ -1638,6 +1869,14 @@ k_unsuitable(const UnsArgs a) {
         uint4 rec = make_uint4(0, 0, 0, 0);
         if (gl < ng) rec = __ldg(&a.inv[g0 + gl]);
         Lane L; L.load(rec, gl < ng);
+        if (a.exhaustive) {                                               // spec §12
+            if (cnt > DRA_MAX_POD || ng > W) continue;
+            const PodGet pget{a.claims + c0, nullptr, 0};
+            Lane Lt = L;                                                    // by copy: a reference would pin L in local memory
+            const uint32_t st = pod_eval<W>(Lt, lane, gmask, gbase, g0, tbl_s, pget, cnt, a.sel, true, true, nullptr);
+            if (st == 0 && gl == 0) atomicOr(&a.bits[pair >> 5], 1u << (pair & 31));
+            continue;
+        }
         Dead D; FlagSink sink; GlobalGet get{a.claims + c0};
         if (ng > W) sink.failed = true;                                   // cannot happen: W is chosen from the inventory
         uint32_t k = 0;

@@ -30,6 +30,8 @@ static const char* status_text(uint8_t st) {
         case DRA_ST_GROUP: return "co-located MIG devices do not fit on one parent GPU";
         case DRA_ST_MEM_LIMIT: return "no shareable GPU with enough free memory";
         case DRA_ST_INVALID: return "invalid claim";
+        case DRA_ST_POD: return "the pod's claims do not fit on the selected node together";
+        case DRA_ST_SEARCH_LIMIT: return "placement search budget exhausted";
         default: return "";
     }
 }
@@ -162,12 +164,34 @@ void Driver::lift(const Lowered& lo, const std::vector<dra_out_rec>& out, bool c
     }
 }
 
+
+// Claims of one pod in lowering order: members of a co-location group (same GpuClaimName) made ADJACENT, in order of
+// the group's first appearance.  The device only co-locates CONSECUTIVE claims with equal group (spec §6); members
+// separated by another claim would be independent runs that may land on different parents while still reporting
+// success — a silent violation of matchAttribute parentUUID (gpu-test4.yaml:42-44).
+static std::vector<ClaimAllocation*> groupAdjacent(const std::vector<ClaimAllocation*>& claims) {
+    std::vector<std::vector<ClaimAllocation*>> runs;
+    std::map<std::string, size_t> runOf;
+    for (ClaimAllocation* ca : claims) {
+        if (ca->IsMig && !ca->Mig.GpuClaimName.empty()) {
+            auto it = runOf.find(ca->Mig.GpuClaimName);
+            if (it != runOf.end()) { runs[it->second].push_back(ca); continue; }
+            runOf[ca->Mig.GpuClaimName] = runs.size();
+        }
+        runs.push_back({ca});
+    }
+    std::vector<ClaimAllocation*> out;
+    for (auto& r : runs) out.insert(out.end(), r.begin(), r.end());
+    return out;
+}
+
 void Driver::AllocateBatch(const std::vector<PodRequest>& pods) {
     Lowered lo;
+    std::vector<uint32_t> podOff(1, 0);                          // pod mode (spec §12): one pod per PodRequest
     for (const auto& pod : pods) {
         const uint32_t node = nodeIndex(pod.SelectedNode);
         std::map<std::string, uint32_t> groups;
-        for (ClaimAllocation* ca : pod.Claims) {
+        for (ClaimAllocation* ca : groupAdjacent(pod.Claims)) {
             if (node == 0xFFFFFFFFu) { ca->Error = "unknown node '" + pod.SelectedNode + "'"; ca->Allocation.clear(); continue; }
             uint32_t g = 0;
             if (ca->IsMig && !ca->Mig.GpuClaimName.empty()) {
@@ -177,10 +201,15 @@ void Driver::AllocateBatch(const std::vector<PodRequest>& pods) {
             }
             lower(*ca, node, g, lo, nodeModel_[node]);
         }
+        podOff.push_back((uint32_t)lo.recs.size());
     }
     if (lo.recs.empty()) return;
     std::vector<dra_out_rec> out(lo.nOut);
-    check(dra_allocate_batch(ctx_, lo.recs.data(), (uint32_t)lo.recs.size(), lo.outOff.data(), out.data(), lo.nOut, 0), "dra_allocate_batch");
+    if (exhaustive_)
+        check(dra_allocate_pods_batch(ctx_, lo.recs.data(), (uint32_t)lo.recs.size(), podOff.data(), (uint32_t)podOff.size() - 1,
+                                      lo.outOff.data(), out.data(), lo.nOut, DRA_F_EXHAUSTIVE), "dra_allocate_pods_batch");
+    else
+        check(dra_allocate_batch(ctx_, lo.recs.data(), (uint32_t)lo.recs.size(), lo.outOff.data(), out.data(), lo.nOut, 0), "dra_allocate_batch");
     lift(lo, out, true);
 }
 
@@ -203,7 +232,7 @@ void Driver::UnsuitableNodesBatch(const std::vector<PodRequest>& pods) {
         bool ok = true;
         const size_t mark = lo.recs.size();
         const uint32_t markOut = lo.nOut;
-        for (ClaimAllocation* ca : pod.Claims) {
+        for (ClaimAllocation* ca : groupAdjacent(pod.Claims)) {
             uint32_t g = 0;
             if (ca->IsMig && !ca->Mig.GpuClaimName.empty()) {
                 auto it = groups.find(ca->Mig.GpuClaimName);
@@ -225,7 +254,7 @@ void Driver::UnsuitableNodesBatch(const std::vector<PodRequest>& pods) {
     if (podOf.empty()) return;
     std::vector<uint8_t> bits((cand.size() + 7) / 8 + 1, 0);
     check(dra_unsuitable_batch(ctx_, lo.recs.data(), (uint32_t)lo.recs.size(), podOff.data(), (uint32_t)podOf.size(),
-                               cand.data(), candOff.data(), bits.data()), "dra_unsuitable_batch");
+                               cand.data(), candOff.data(), bits.data(), exhaustive_ ? DRA_F_EXHAUSTIVE : 0u), "dra_unsuitable_batch");
     for (size_t q = 0; q < podOf.size(); ++q) {
         const auto& pod = pods[podOf[q]];
         for (uint32_t k = candOff[q]; k < candOff[q + 1]; ++k) {

@@ -21,9 +21,13 @@ KIND_GPU, KIND_MIG, KIND_SHARED = 0, 1, 2
 GPU_MIG_ENABLED, GPU_FULL_ALLOCATED, GPU_UNAVAILABLE = 0x01, 0x02, 0x04
 PROFILE_GPU, PROFILE_SHARED = 0xFF, 0xFE
 ST_OK, ST_NO_CAPACITY, ST_BAD_PROFILE, ST_GROUP, ST_MEM_LIMIT, ST_INVALID = 0, 1, 2, 3, 4, 5
-STATUS_NAMES = {0: "OK", 1: "NO_CAPACITY", 2: "BAD_PROFILE", 3: "GROUP", 4: "MEM_LIMIT", 5: "INVALID"}
+ST_POD, ST_SEARCH_LIMIT = 6, 7            # pod mode (spec §12)
+MAX_POD, EXH_BUDGET = 32, 4096
+STATUS_NAMES = {0: "OK", 1: "NO_CAPACITY", 2: "BAD_PROFILE", 3: "GROUP", 4: "MEM_LIMIT", 5: "INVALID", 6: "POD",
+                7: "SEARCH_LIMIT"}
 
 F_NODE_SORTED = 0x1
+F_EXHAUSTIVE = 0x4
 
 GPU_DTYPE = np.dtype([("busy", "<u2"), ("flags", "u1"), ("model", "u1"), ("mem_free_mib", "<u4"),
                       ("node", "<u4"), ("share_cnt", "<u2"), ("rsvd", "<u2")])

@@ -285,3 +285,30 @@ def homog(n_claim: int = 3000, n_node: int = 24, seed: int = 1, model: int = 0, 
     c["profile"] = profs[(b[0::2] % np.uint64(len(profs))).astype(np.int64)]
     c["node"] = (b[1::2] % np.uint64(n_node)).astype(np.uint32)
     return Workload(f"homog{seed}", g, off, t, c).finish()
+
+
+def pods(n_pod: int = 20_000, n_node: int = 64, seed: int = 0, gpus_per_node: int = 8, max_claims: int = 5,
+         grouped: bool = True):
+    """Pod-mode workload (spec §12): pods of 1..max_claims MIG claims of mixed profiles (the multi-request shape of
+    demo/specs/quickstart/gpu-test4.yaml:19-44) over cfg5's pre-fragmented inventory — the regime where in-order
+    first-fit gives false negatives.  ~1/4 of the multi-claim pods carry a co-location group (matchAttribute
+    parentUUID).  Returns (Workload, pod_off)."""
+    g, off = R.make_inventory([gpus_per_node] * n_node, mig=True)
+    r = splitmix64(BASE_SEED + 500 + seed, len(g) + 3 * n_pod + n_pod * max_claims + 8)
+    g["busy"] = _FRAG[(r[: len(g)] % np.uint64(len(_FRAG))).astype(np.int64)]
+    a = r[len(g):]
+    sizes = 1 + (a[:n_pod] % np.uint64(max_claims)).astype(np.int64)
+    nodes = (a[n_pod: 2 * n_pod] % np.uint64(n_node)).astype(np.uint32)
+    grp = (a[2 * n_pod: 3 * n_pod] % np.uint64(4) == 0) & (sizes > 1) if grouped else np.zeros(n_pod, bool)
+    pod_off = np.zeros(n_pod + 1, dtype=np.uint32)
+    pod_off[1:] = np.cumsum(sizes)
+    n_claim = int(pod_off[-1])
+    c = np.zeros(n_claim, dtype=R.CLAIM_DTYPE)
+    c["kind"], c["count"] = R.KIND_MIG, 1
+    pick = (a[3 * n_pod: 3 * n_pod + n_claim] % np.uint64(100)).astype(np.int64)
+    c["profile"] = np.where(pick < 45, R.GI_1_SLICE, np.where(pick < 75, R.GI_2_SLICE,
+                            np.where(pick < 97, R.GI_3_SLICE, R.GI_7_SLICE)))
+    c["node"] = np.repeat(nodes, sizes)
+    c["group"] = np.repeat(np.where(grp, np.arange(1, n_pod + 1, dtype=np.uint32), 0).astype(np.uint32), sizes)
+    w = Workload(f"pods{seed}", g, off, R.default_table(), c).finish()
+    return w, pod_off

@@ -549,6 +549,177 @@ int dra_oracle_unsuitable(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_
     return 0;
 }
 
+/* ---- spec §12: pod mode and the exhaustive placement search ------------------------------------------------
+ * The enumeration that is searched is the (profile, placement) list deviceLib.getGpuInfo collects per GPU
+ * (cmd/nvidia-dra-plugin/nvlib.go:244-295); the multi-request shape is demo/specs/quickstart/gpu-test4.yaml:19-44;
+ * the search itself follows the recollected classic mig.allocate — PARITY UNPINNED. */
+
+typedef struct pod_search {
+    dra_gpu_rec* gpus; uint32_t g0, ng;
+    const dra_profile_tbl* tbl;
+    const dra_claim_rec* claims;        /* the pod's claims */
+    const uint32_t* mig; uint32_t k;    /* positions of the MIG claims inside the pod */
+    int exhaustive;
+    uint32_t descents; int limit_hit;
+    int gpu_of[DRA_MAX_POD], start_of[DRA_MAX_POD];     /* per level */
+} pod_search;
+
+/* level i: canonical order = GPUs ascending, starts ascending; returns 1 when levels i.. are all placed */
+static int pod_dfs(pod_search* ps, uint32_t i)
+{
+    if (i == ps->k) return 1;
+    const dra_claim_rec* c = &ps->claims[ps->mig[i]];
+    int want_gpu = -1;                                  /* co-location: the GPU of the first earlier member */
+    if (c->group != 0)
+        for (uint32_t j = 0; j < i; j++)
+            if (ps->claims[ps->mig[j]].group == c->group) { want_gpu = ps->gpu_of[j]; break; }
+    for (uint32_t g = 0; g < ps->ng; g++) {
+        if (want_gpu >= 0 && (int)g != want_gpu) continue;
+        dra_gpu_rec* r = &ps->gpus[g];
+        dra_prof_ent e = ps->tbl[r->model].ent[c->profile];
+        if (!gpu_offers(r, e) || (r->flags & DRA_GPU_FULL_ALLOCATED)) continue;
+        if (!sel_pass(claim_sel(c), ps->g0 + g)) continue;
+        for (int s = 0; s < 16; s++) {
+            if (!((e.start_mask >> s) & 1u)) continue;
+            uint16_t m = (uint16_t)(((1u << e.size) - 1u) << s);
+            if (r->busy & m) continue;
+            if (ps->descents == DRA_EXH_BUDGET) { ps->limit_hit = 1; return 0; }
+            ps->descents++;
+            r->busy |= m; ps->gpu_of[i] = (int)g; ps->start_of[i] = s;
+            if (pod_dfs(ps, i + 1)) return 1;
+            r->busy &= (uint16_t)~m;
+            if (ps->limit_hit || !ps->exhaustive) return 0;      /* first-fit: the first branch only */
+        }
+    }
+    return 0;
+}
+
+/* Evaluate one pod on the node whose GPUs are gpus[0..ng) (mutated only on success).  claims[0..cnt) are the
+ * pod's claims (node already validated / overridden by the caller), slot[i] = first OutRec of claim i in out
+ * (out may be NULL: evaluate only).  Returns 1 when the pod was placed. */
+static int pod_eval(dra_gpu_rec* gpus, uint32_t g0, uint32_t ng, const dra_profile_tbl* tbl,
+                    const dra_claim_rec* claims, uint32_t cnt, uint32_t n_node, int have_off,
+                    const uint32_t* slot, dra_out_rec* out, int exhaustive)
+{
+    dra_out_rec scratch[DRA_MAX_POD * DRA_MAX_COUNT];
+    uint32_t sslot[DRA_MAX_POD];
+    if (!out) {                                          /* evaluate only: private slots */
+        uint32_t t = 0;
+        for (uint32_t i = 0; i < cnt; i++) { sslot[i] = t; t += claim_slots(&claims[i], n_node, have_off); }
+        out = scratch; slot = sslot;
+    }
+    int any_invalid = 0;
+    for (uint32_t i = 0; i < cnt; i++) if (claim_invalid(&claims[i], n_node, have_off)) any_invalid = 1;
+    uint8_t fail_st = DRA_ST_POD;
+    int ok = !any_invalid;
+    dra_gpu_rec work[DRA_MAX_GPUS_PER_NODE];
+    memcpy(work, gpus, ng * sizeof(dra_gpu_rec));
+    uint32_t mig[DRA_MAX_POD], k = 0;
+    if (ok) {                                            /* step 2: GPU and SHARED claims, in order, §4 / §7 */
+        uint32_t idx[DRA_MAX_POD];
+        for (uint32_t i = 0; i < cnt; i++) idx[i] = i;
+        node_job j; memset(&j, 0, sizeof j);
+        j.gpus = work; j.g0 = g0; j.ng = ng; j.tbl = tbl; j.claims = claims; j.idx = idx; j.cnt = cnt;
+        j.n_node = n_node; j.out_off = slot; j.out = out; j.all_ok = 1;
+        for (uint32_t i = 0; i < cnt && j.all_ok; i++) {
+            if (claims[i].kind == DRA_KIND_GPU) do_gpu(&j, i);
+            else if (claims[i].kind == DRA_KIND_SHARED) do_shared(&j, i);
+            else mig[k++] = i;
+        }
+        ok = j.all_ok;
+    }
+    pod_search ps; memset(&ps, 0, sizeof ps);
+    if (ok && k) {                                       /* step 3: the MIG claims, canonical DFS */
+        ps.gpus = work; ps.g0 = g0; ps.ng = ng; ps.tbl = tbl; ps.claims = claims; ps.mig = mig; ps.k = k;
+        ps.exhaustive = exhaustive;
+        ok = pod_dfs(&ps, 0);
+        if (!ok && ps.limit_hit) fail_st = DRA_ST_SEARCH_LIMIT;
+    }
+    if (ok) {
+        for (uint32_t i = 0; i < k; i++) {
+            const dra_claim_rec* c = &claims[mig[i]];
+            dra_prof_ent e = tbl[work[ps.gpu_of[i]].model].ent[c->profile];
+            put(&out[slot[mig[i]]], g0 + (uint32_t)ps.gpu_of[i], (uint8_t)ps.start_of[i], e.size, c->profile, DRA_ST_OK);
+        }
+        memcpy(gpus, work, ng * sizeof(dra_gpu_rec));
+        return 1;
+    }
+    for (uint32_t i = 0; i < cnt; i++) {
+        int inv = claim_invalid(&claims[i], n_node, have_off);
+        fail_all(&out[slot[i]], claim_slots(&claims[i], n_node, have_off), &claims[i], inv ? DRA_ST_INVALID : fail_st);
+    }
+    return 0;
+}
+
+int dra_oracle_allocate_pods(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node,
+                             const dra_profile_tbl* tbl, const dra_claim_rec* claims, uint32_t n_claim,
+                             const uint32_t* pod_off, uint32_t n_pod,
+                             const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, uint32_t flags)
+{
+    if (check_inventory(gpus, n_gpu, node_off, n_node, tbl)) return -1;
+    if (pod_off[0] != 0 || pod_off[n_pod] != n_claim) return -1;
+    int have_off = out_off != NULL;
+    uint32_t* slot = (uint32_t*)malloc(((size_t)n_claim + 1) * sizeof(uint32_t));
+    if (!slot) return -1;
+    for (uint32_t i = 0; i < n_claim; i++) {
+        slot[i] = have_off ? out_off[i] : i;
+        uint32_t sl = claim_slots(&claims[i], n_node, have_off);
+        if (slot[i] > n_out || sl > n_out - slot[i]) { free(slot); return -1; }
+    }
+    /* pods in input order; a pod touches one node only, so "per node in input order" is just input order */
+    for (uint32_t p = 0; p < n_pod; p++) {
+        uint32_t c0 = pod_off[p], c1 = pod_off[p + 1];
+        if (c1 < c0) { free(slot); return -1; }
+        uint32_t cnt = c1 - c0;
+        if (cnt == 0) continue;
+        uint32_t node = claims[c0].node;
+        int malformed = cnt > DRA_MAX_POD || node >= n_node;
+        for (uint32_t i = c0; i < c1 && !malformed; i++) if (claims[i].node != node) malformed = 1;
+        if (malformed) {
+            for (uint32_t i = c0; i < c1; i++)
+                fail_all(&out[slot[i]], claim_slots(&claims[i], n_node, have_off), &claims[i], DRA_ST_INVALID);
+            continue;
+        }
+        pod_eval(gpus + node_off[node], node_off[node], node_off[node + 1] - node_off[node], tbl,
+                 claims + c0, cnt, n_node, have_off, slot + c0, out, (flags & DRA_F_EXHAUSTIVE) != 0);
+    }
+    free(slot);
+    return 0;
+}
+
+/* spec §12: UnsuitableNodes with DRA_F_EXHAUSTIVE — a node is unsuitable only if NO assignment of the pod exists */
+int dra_oracle_unsuitable_ex(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off,
+                             uint32_t n_node, const dra_profile_tbl* tbl,
+                             const dra_claim_rec* claims, uint32_t n_claim,
+                             const uint32_t* pod_off, uint32_t n_pod,
+                             const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits,
+                             uint32_t flags)
+{
+    if (!(flags & DRA_F_EXHAUSTIVE))
+        return dra_oracle_unsuitable(gpus, n_gpu, node_off, n_node, tbl, claims, n_claim, pod_off, n_pod,
+                                     cand_nodes, cand_off, suitable_bits);
+    if (check_inventory(gpus, n_gpu, node_off, n_node, tbl)) return -1;
+    if (pod_off[n_pod] != n_claim) return -1;
+    uint32_t n_pair = cand_off[n_pod];
+    memset(suitable_bits, 0, ((size_t)n_pair + 7) / 8);
+    for (uint32_t p = 0; p < n_pod; p++) {
+        uint32_t c0 = pod_off[p], cnt = pod_off[p + 1] - pod_off[p];
+        if (cnt > DRA_MAX_POD) continue;                          /* unsuitable everywhere */
+        for (uint32_t kk = cand_off[p]; kk < cand_off[p + 1]; kk++) {
+            uint32_t n = cand_nodes[kk];
+            if (n >= n_node) continue;
+            dra_claim_rec pod[DRA_MAX_POD];
+            for (uint32_t i = 0; i < cnt; i++) { pod[i] = claims[c0 + i]; pod[i].node = n; }
+            dra_gpu_rec snap[DRA_MAX_GPUS_PER_NODE];
+            uint32_t ng = node_off[n + 1] - node_off[n];
+            memcpy(snap, gpus + node_off[n], ng * sizeof(dra_gpu_rec));
+            if (pod_eval(snap, node_off[n], ng, tbl, pod, cnt, n_node, 1, NULL, NULL, 1))
+                suitable_bits[kk >> 3] |= (uint8_t)(1u << (kk & 7));
+        }
+    }
+    return 0;
+}
+
 /* spec §9 */
 int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu, uint32_t n_node,
                           const dra_claim_rec* claims, uint32_t n_claim,

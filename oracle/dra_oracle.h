@@ -44,6 +44,19 @@ int dra_oracle_unsuitable(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_
                           const uint32_t* pod_off, uint32_t n_pod,
                           const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits);
 
+/* Pod mode (spec §12): Allocate with pod boundaries, atomic per pod; flags & DRA_F_EXHAUSTIVE = backtracking search. */
+int dra_oracle_allocate_pods(dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node,
+                             const dra_profile_tbl* tbl, const dra_claim_rec* claims, uint32_t n_claim,
+                             const uint32_t* pod_off, uint32_t n_pod,
+                             const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, uint32_t flags);
+/* UnsuitableNodes with flags (DRA_F_EXHAUSTIVE: spec §12; 0: spec §8, same as dra_oracle_unsuitable). */
+int dra_oracle_unsuitable_ex(const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off,
+                             uint32_t n_node, const dra_profile_tbl* tbl,
+                             const dra_claim_rec* claims, uint32_t n_claim,
+                             const uint32_t* pod_off, uint32_t n_pod,
+                             const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits,
+                             uint32_t flags);
+
 /* Deallocate (spec §9). */
 int dra_oracle_deallocate(dra_gpu_rec* gpus, uint32_t n_gpu, uint32_t n_node,
                           const dra_claim_rec* claims, uint32_t n_claim,

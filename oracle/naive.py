@@ -159,3 +159,166 @@ def allocate(gpus, node_off, table, claims, out_off=None):
                       "flags": (1 if g["mig"] else 0) | (2 if g["full"] else 0) | (4 if g["unavail"] else 0),
                       "model": g["model"], "mem_free_mib": g["mem"], "share_cnt": g["share"]})
     return out, after
+
+
+# ---- spec §12: pod mode + exhaustive placement search ---------------------------------------------------------
+EXH_BUDGET = 4096
+MAX_POD = 32
+
+
+class _Limit(Exception):
+    pass
+
+
+def _state(gpus):
+    return [{"used": {i for i in range(16) if (g["busy"] >> i) & 1}, "mig": bool(g["flags"] & 1),
+             "full": bool(g["flags"] & 2), "unavail": bool(g["flags"] & 4), "model": g["model"],
+             "mem": g["mem_free_mib"], "share": g["share_cnt"]} for g in gpus]
+
+
+def _dump(gpus, G):
+    return [{"busy": sum(1 << s for s in g["used"]),
+             "flags": (1 if g["mig"] else 0) | (2 if g["full"] else 0) | (4 if g["unavail"] else 0),
+             "model": g["model"], "mem_free_mib": g["mem"], "share_cnt": g["share"]} for g in G]
+
+
+def eval_pod(G, g0, g1, table, pod, n_node, exhaustive, have_off=True):
+    """One pod on the GPUs G[g0:g1] (list of state dicts, mutated only on success).
+    Returns (placed, per-claim list of record lists)."""
+    import copy
+    inv = [_invalid(c, n_node, have_off) for c in pod]
+    sl = [_slots(c, n_node, have_off) for c in pod]
+
+    def failed(st):
+        return False, [[(NONE, 0, 0, _oprof(c), 5 if bad else st)] * n for c, bad, n in zip(pod, inv, sl)]
+
+    if any(inv):
+        return failed(6)
+    W = copy.deepcopy(G[g0:g1])
+    recs = [None] * len(pod)
+    for i, c in enumerate(pod):                       # step 2: GPU / SHARED claims in order
+        if c["kind"] == 0:
+            el = [k for k, g in enumerate(W) if not (g["mig"] or g["full"] or g["unavail"]) and g["share"] == 0]
+            if len(el) < c["count"]:
+                return failed(6)
+            for k in el[: c["count"]]:
+                W[k]["full"] = True
+            recs[i] = [(g0 + k, 0, 0, 0xFF, 0) for k in el[: c["count"]]]
+        elif c["kind"] == 2:
+            for k, g in enumerate(W):
+                if g["mig"] or g["full"] or g["unavail"] or g["share"] == 0xFFFF or g["mem"] < c["mem_limit_mib"]:
+                    continue
+                g["mem"] -= c["mem_limit_mib"]
+                g["share"] += 1
+                recs[i] = [(g0 + k, 0, 0, 0xFE, 0)]
+                break
+            else:
+                return failed(6)
+    mig = [i for i, c in enumerate(pod) if c["kind"] == 1]
+    budget = [0]
+    choice = {}
+
+    def options(level):
+        c = pod[mig[level]]
+        want = None
+        if c["group"]:
+            for j in range(level):
+                if pod[mig[j]]["group"] == c["group"]:
+                    want = choice[j][0]
+                    break
+        for k, g in enumerate(W):
+            if want is not None and k != want:
+                continue
+            size, mask = table[g["model"]][c["profile"]]
+            if not g["mig"] or g["unavail"] or g["full"] or not mask:
+                continue
+            for s in range(16):
+                if (mask >> s) & 1 and not (set(range(s, s + size)) & g["used"]):
+                    yield k, s, size
+
+    def search(level):
+        if level == len(mig):
+            return True
+        for k, s, size in options(level):
+            if budget[0] == EXH_BUDGET:
+                raise _Limit
+            budget[0] += 1
+            W[k]["used"] |= set(range(s, s + size))
+            choice[level] = (k, s, size)
+            if search(level + 1):
+                return True
+            W[k]["used"] -= set(range(s, s + size))
+            if not exhaustive:
+                return False
+        return False
+
+    try:
+        ok = search(0)
+    except _Limit:
+        return failed(7)
+    if not ok:
+        return failed(6)
+    for level, i in enumerate(mig):
+        k, s, size = choice[level]
+        recs[i] = [(g0 + k, s, size, pod[i]["profile"], 0)]
+    G[g0:g1] = W
+    return True, recs
+
+
+def allocate_pods(gpus, node_off, table, claims, pod_off, exhaustive, out_off=None):
+    """spec §12.  Returns (out list, gpus_after)."""
+    n_node = len(node_off) - 1
+    have_off = out_off is not None
+    G = _state(gpus)
+    sl = [_slots(c, n_node, have_off) for c in claims]
+    base = list(out_off) if have_off else list(range(len(claims)))
+    n_out = max([b + s for b, s in zip(base, sl)], default=0)
+    out = [None] * n_out
+    for p in range(len(pod_off) - 1):
+        c0, c1 = pod_off[p], pod_off[p + 1]
+        pod = claims[c0:c1]
+        if not pod:
+            continue
+        node = pod[0]["node"]
+        if len(pod) > MAX_POD or node >= n_node or any(c["node"] != node for c in pod):
+            for i in range(c0, c1):
+                for k in range(sl[i]):
+                    out[base[i] + k] = (NONE, 0, 0, _oprof(claims[i]), 5)
+            continue
+        _, recs = eval_pod(G, node_off[node], node_off[node + 1], table, pod, n_node, exhaustive, have_off)
+        for i, r in zip(range(c0, c1), recs):
+            for k, rec in enumerate(r):
+                out[base[i] + k] = rec
+    return out, _dump(gpus, G)
+
+
+def pod_fits_bruteforce(gpus, table, pod):
+    """Third opinion for tiny pods of MIG claims without selectors: does ANY assignment exist?  Enumerates every
+    (gpu, start) vector with itertools.product — no pruning, no order."""
+    import itertools
+    G = _state(gpus)
+    opts = []
+    for c in pod:
+        o = []
+        for k, g in enumerate(G):
+            size, mask = table[g["model"]][c["profile"]]
+            if not g["mig"] or g["unavail"] or g["full"]:
+                continue
+            o += [(k, s, size) for s in range(16) if (mask >> s) & 1]
+        opts.append(o)
+    for vec in itertools.product(*opts):
+        used = [set(g["used"]) for g in G]
+        ok = True
+        grp = {}
+        for c, (k, s, size) in zip(pod, vec):
+            if c["group"] and grp.setdefault(c["group"], k) != k:
+                ok = False
+                break
+            cells = set(range(s, s + size))
+            if cells & used[k]:
+                ok = False
+                break
+            used[k] |= cells
+        if ok:
+            return True
+    return False

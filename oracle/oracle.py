@@ -48,6 +48,10 @@ def lib():
         _lib.dra_oracle_allocate_mt.restype = i32
         _lib.dra_oracle_unsuitable.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, u32, vp, vp, vp]
         _lib.dra_oracle_unsuitable.restype = i32
+        _lib.dra_oracle_allocate_pods.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, u32, vp, vp, u32, u32]
+        _lib.dra_oracle_allocate_pods.restype = i32
+        _lib.dra_oracle_unsuitable_ex.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, u32, vp, vp, vp, u32]
+        _lib.dra_oracle_unsuitable_ex.restype = i32
         _lib.dra_oracle_deallocate.argtypes = [vp, u32, u32, vp, u32, vp, vp, u32]
         _lib.dra_oracle_deallocate.restype = i32
         _lib.dra_oracle_set_selectors.argtypes = [vp, u32, vp, u32]
@@ -85,7 +89,30 @@ def allocate(gpus, node_off, table, claims, out_off=None, n_out=None, threads: i
     return out[:n_out], g
 
 
-def unsuitable(gpus, node_off, table, claims, pod_off, cand_nodes, cand_off):
+F_EXHAUSTIVE = 0x4
+
+
+def allocate_pods(gpus, node_off, table, claims, pod_off, out_off=None, n_out=None, flags: int = 0):
+    """spec §12 (pod mode).  Returns (out, gpus_after)."""
+    g = _c(gpus, GPU_DTYPE).copy()
+    off = _c(node_off, np.uint32)
+    t = np.ascontiguousarray(table)
+    c = _c(claims, CLAIM_DTYPE)
+    po = _c(pod_off, np.uint32)
+    oo = None if out_off is None else _c(out_off, np.uint32)
+    if n_out is None:
+        n_out = len(c) if oo is None else 0
+    out = np.zeros(max(n_out, 1), dtype=OUT_DTYPE)
+    rc = lib().dra_oracle_allocate_pods(_p(g), len(g), _p(off), len(off) - 1, _p(t), _p(c), len(c), _p(po), len(po) - 1,
+                                        _p(oo), _p(out), n_out, flags)
+    if rc != 0:
+        raise ValueError(f"dra_oracle_allocate_pods: rc={rc}")
+    return out[:n_out], g
+
+
+def unsuitable(gpus, node_off, table, claims, pod_off, cand_nodes, cand_off, flags: int = 0):
+    if flags:
+        return _unsuitable_ex(gpus, node_off, table, claims, pod_off, cand_nodes, cand_off, flags)
     g = _c(gpus, GPU_DTYPE)
     off = _c(node_off, np.uint32)
     t = np.ascontiguousarray(table)
@@ -99,6 +126,23 @@ def unsuitable(gpus, node_off, table, claims, pod_off, cand_nodes, cand_off):
                                      _p(po), len(po) - 1, _p(cn), _p(co), _p(bits))
     if rc != 0:
         raise ValueError(f"dra_oracle_unsuitable: rc={rc}")
+    return bits[: (n_pair + 7) // 8]
+
+
+def _unsuitable_ex(gpus, node_off, table, claims, pod_off, cand_nodes, cand_off, flags):
+    g = _c(gpus, GPU_DTYPE)
+    off = _c(node_off, np.uint32)
+    t = np.ascontiguousarray(table)
+    c = _c(claims, CLAIM_DTYPE)
+    po = _c(pod_off, np.uint32)
+    cn = _c(cand_nodes, np.uint32)
+    co = _c(cand_off, np.uint32)
+    n_pair = int(co[-1])
+    bits = np.zeros((n_pair + 7) // 8 + 1, dtype=np.uint8)
+    rc = lib().dra_oracle_unsuitable_ex(_p(g), len(g), _p(off), len(off) - 1, _p(t), _p(c), len(c),
+                                        _p(po), len(po) - 1, _p(cn), _p(co), _p(bits), flags)
+    if rc != 0:
+        raise ValueError(f"dra_oracle_unsuitable_ex: rc={rc}")
     return bits[: (n_pair + 7) // 8]
 
 
