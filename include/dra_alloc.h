@@ -277,8 +277,8 @@ int  dra_gather_table(dra_ctx* ctx, const dra_out_rec** d_table, uint32_t* n_per
 /* Device -> host read of the first n_rec records of that table on ctx's stream, then synchronises. */
 int  dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec);
 
-/* Peer-memory all-gather (NVLink P2P stores + epoch flags) — when set up, dra_allocate_batch_gather_device
- * uses it instead of ncclAllGather.  Call after dra_comm_init on every rank:
+/* Peer-memory all-gather (OutRecs as self-validating 16-byte packets over NVLink, no fence / flag; measurements in
+ * profiles/peer_bench_r02.txt) — when set up, dra_allocate_batch_gather_device uses it instead of ncclAllGather.  Call after dra_comm_init on every rank:
  *   dra_peer_export(ctx, n_per_rank, handle)   allocates this rank's gather buffer, returns its 64-byte
  *                                              cudaIpcMemHandle_t;  the host runtime all-gathers the handles;
  *   dra_peer_import(ctx, handles)              world * 64 bytes, in rank order.
@@ -286,6 +286,32 @@ int  dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec);
  * dra_peer_export(ctx, 0, NULL) switches the peer path off again. */
 int  dra_peer_export(dra_ctx* ctx, uint32_t n_per_rank, void* handle64);
 int  dra_peer_import(dra_ctx* ctx, const void* handles);
+
+/* The same mapping for contexts of ONE process (one Go driver process driving all GPUs of a box, or tests): instead of
+ * NCCL + IPC handles, call dra_comm_init_local(ctx, rank, world) on every context, dra_peer_export / dra_shard_export
+ * (handle may be NULL), then dra_peer_import_local(ctx, ctxs) with the world contexts in rank order (peer access between
+ * their devices is enabled here).  Calls of different ranks must then be issued without waiting for each other. */
+int  dra_comm_init_local(dra_ctx* ctx, int rank, int world);
+int  dra_peer_import_local(dra_ctx* ctx, dra_ctx* const* ctxs);
+
+/* ---- sharded GLOBAL batch (BASELINE configs[2]: one batch, claim x node space sharded over the GPUs of a box) -----
+ * Every rank loads the WHOLE inventory (dra_set_inventory) and serves a contiguous node range
+ * (dra_set_shard; pool = node, nodes are never split: vendor/k8s.io/dynamic-resource-allocation/kubeletplugin/
+ * draplugin.go:427-435).  dra_allocate_batch_global_device takes the SAME global claim array on every rank: the rank
+ * filters the claims of its nodes on the device (stable compaction in input order), allocates them, and writes each
+ * OutRec at the claim's GLOBAL slot of every rank's result table — the path's one collective, an all-gather done as
+ * 16-byte self-validating packets over NVLink inside the allocation kernel (no host partition / merge, no un-permute).
+ * Claims that name no node are answered by the rank with take_stray != 0 (exactly one rank).
+ *   dra_shard_export(ctx, n_out_max, cap_per_rank, handle)  allocates table + staging (cap_per_rank = upper bound of the
+ *        OutRec slots one rank can own, 0 = n_out_max); handles are exchanged and mapped with dra_peer_import as above
+ *   result: dra_gather_table / dra_gather_read (n_out records, input order, global GPU indices)
+ * out_off must tile [0, n_out) (slots no claim owns keep their previous contents).  flags: DRA_F_FRESH_INVENTORY.
+ * With world == 1 no export is needed (the table is local).  A rank's live inventory is authoritative for its own
+ * node range only. */
+int  dra_set_shard(dra_ctx* ctx, uint32_t node_lo, uint32_t node_hi, int take_stray);
+int  dra_shard_export(dra_ctx* ctx, uint32_t n_out_max, uint32_t cap_per_rank, void* handle64);
+int  dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim,
+                                      const uint32_t* d_out_off, uint32_t n_out, uint32_t flags);
 
 /* ---- adjacent integer searches of the reference, batched (API completeness) -------------- */
 

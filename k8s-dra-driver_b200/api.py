@@ -56,6 +56,11 @@ SYMBOLS = {
     "dra_gather_read": (_i32, [_vp, _vp, _u32]),
     "dra_peer_export": (_i32, [_vp, _u32, _vp]),
     "dra_peer_import": (_i32, [_vp, _vp]),
+    "dra_comm_init_local": (_i32, [_vp, _i32, _i32]),
+    "dra_peer_import_local": (_i32, [_vp, _vp]),
+    "dra_set_shard": (_i32, [_vp, _u32, _u32, _i32]),
+    "dra_shard_export": (_i32, [_vp, _u32, _u32, _vp]),
+    "dra_allocate_batch_global_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32]),
     "dra_mps_limits_batch": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "dra_imex_offsets_batch": (_i32, [_vp, _vp, _vp, _u32, C.c_int32, C.c_int32, _vp]),
     "dra_host_alloc": (_vp, [C.c_size_t]),
@@ -314,6 +319,28 @@ class Context:
         buf = (C.c_uint8 * 64)()
         self._check(self._lib.dra_peer_export(self._h, n_per_rank, C.cast(buf, C.c_void_p)))
         return bytes(buf)
+
+    def comm_init_local(self, rank: int, world: int) -> None:
+        """Rank / world of a context whose peers live in THIS process (no NCCL communicator)."""
+        self._check(self._lib.dra_comm_init_local(self._h, rank, world))
+
+    def peer_import_local(self, ctxs) -> None:
+        """Map the gather buffers of the world contexts of this process (rank order)."""
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        self._check(self._lib.dra_peer_import_local(self._h, C.cast(arr, C.c_void_p)))
+
+    def set_shard(self, node_lo: int, node_hi: int, take_stray: bool = False) -> None:
+        self._check(self._lib.dra_set_shard(self._h, node_lo, node_hi, 1 if take_stray else 0))
+
+    def shard_export(self, n_out_max: int, cap_per_rank: int = 0, want_handle: bool = True) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self._lib.dra_shard_export(self._h, n_out_max, cap_per_rank, C.cast(buf, C.c_void_p) if want_handle else None))
+        return bytes(buf)
+
+    def allocate_global_device(self, d_claims: int, n_claim: int, d_out_off: int | None, n_out: int, flags: int = 0):
+        """Sharded global batch: the SAME claim array on every rank (device pointer); enqueues, no synchronisation.
+        The result table: gather_read()."""
+        self._check(self._lib.dra_allocate_batch_global_device(self._h, _ptr(d_claims), n_claim, _ptr(d_out_off), n_out, flags))
 
     def peer_import(self, handles) -> None:
         blob = b"".join(handles)

@@ -114,6 +114,7 @@ struct dra_ctx {
     uint32_t* d_gbar = nullptr;             // grid barrier words
     int n_sm = 0, coop_ok = 0;
     int dio_cap_smem = -1, dio_cap_cta = 0; // co-resident CTA capacity of k_fused at dio_cap_smem bytes of shared memory
+    int tail_cap_smem = -1, tail_cap_stage = -1, tail_cap_cta = 0;   // the same for the gather tail
     const void* dio_seen[3] = {nullptr, nullptr, nullptr};   // host pointers already checked to be device-visible as-is
 
     ncclComm_t comm = nullptr;
@@ -127,16 +128,28 @@ struct dra_ctx {
     uint32_t graph_launches = 0;
     uint64_t state_epoch = 1;     // bumped by every call that reallocates or re-points device state
 
-    // peer-memory all-gather
+    // peer-memory all-gather (packets over NVLink, dra_device.cuh PktGather)
     bool peer_ready = false;
-    uint32_t peer_n_per = 0, peer_epoch = 0;
-    size_t peer_bytes = 0, peer_flag_off = 0;
-    uint8_t* peer_local = nullptr;              // this rank's buffer (cudaMalloc)
+    uint32_t peer_form = 0;                     // 1: per-rank slices [world][n_per]   2: global slots [tab_len]
+    uint32_t peer_n_per = 0, peer_tab_len = 0, peer_cap = 0, peer_epoch = 0;
+    size_t peer_bytes = 0, off_table[2] = {0, 0}, off_stage[2] = {0, 0}, off_hdr[2] = {0, 0};
+    uint8_t* peer_local = nullptr;              // this rank's buffer (cudaMalloc, exported by IPC handle)
     uint8_t* peer_base[PEER_MAX] = {};          // every rank's buffer as mapped here
+    bool peer_ipc[PEER_MAX] = {};               // mapped with cudaIpcOpenMemHandle (else: same process)
+    uint32_t* d_cursor = nullptr;               // [2] packet reservation cursors (local)
+    long long peer_spin = 4000000000ll;         // cycles a receiver waits for a packet before ERR_PEER_TIMEOUT
+    // sharded global batch
+    bool shard_on = false; uint32_t shard_lo = 0, shard_hi = 0, shard_stray = 0, shard_epoch = 0;
+    uint4* d_cclaims = nullptr; uint32_t* d_coff = nullptr; size_t cap_cclaims = 0;
+    unsigned long long* d_sc_status = nullptr; size_t cap_sc_status = 0;
+    uint32_t* d_sc_counts = nullptr;            // device: [0] claims kept, [1] slots
+    volatile uint32_t* h_sc_counts = nullptr;   // mapped host copy of the last call's counts
+    uint32_t* h_sc_counts_dev = nullptr;
+    uint2* d_gtable = nullptr; size_t cap_gtable = 0;   // result table when no peers are set up (world 1)
     uint32_t* d_ticket = nullptr;
     unsigned long long* d_timeline = nullptr; size_t tl_cap = 0; uint32_t tl_n = 0;
     const dra_out_rec* gather_table = nullptr;  // where the last gather's complete table lives (device)
-    uint32_t gather_n_per = 0;
+    uint32_t gather_n_per = 0, gather_len = 0;   // gather_len != 0: a global table of that many records
 
     std::string err;
 };
@@ -257,9 +270,8 @@ constexpr int FUSED_NW = 8;
 // Which kernel chain an Allocate batch takes.  Small batches: ONE launch — every node's CTA filters the claim
 // stream for itself (n_node * n_claim key tests spread over n_node SMs, data from L2) and packs; no sort, no copy.
 struct FusedPlan { bool fused, stage; size_t smem; };
-FusedPlan fused_plan(const dra_ctx* ctx, uint32_t n_claim, uint32_t flags) {
+FusedPlan fused_plan(const dra_ctx* ctx, uint32_t n_claim, uint32_t flags, uint32_t n_node) {
     static const bool no_stage = getenv("DRA_NO_STAGE") != nullptr;          // experiment switch
-    const uint32_t n_node = ctx->n_node;
     FusedPlan p;
     p.stage = !no_stage && n_claim <= FUSED_NW * FU_PIECE * FU_MAXPIECE && fused_smem_bytes(n_claim, FUSED_NW, true) <= 225 * 1024;
     p.smem = fused_smem_bytes(n_claim, FUSED_NW, p.stage);
@@ -276,12 +288,13 @@ FusedPlan fused_plan(const dra_ctx* ctx, uint32_t n_claim, uint32_t flags) {
 // front half of the sort path.  Records naming no node get an INVALID OutRec (d_out != nullptr) or are dropped
 // (d_out == nullptr: pod records).  Enqueues only.
 int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off, uint2* d_out,
-                uint32_t n_out, uint32_t flags, Prof& prof, const void* inv_src, bool pdl) {
-    const uint32_t n_node = ctx->n_node;
+                uint32_t n_out, uint32_t flags, Prof& prof, const void* inv_src, bool pdl,
+                uint32_t n_node, const uint32_t* d_node_off, const uint32_t* n_dev = nullptr) {
     Err err = err_of(ctx);
     // sort path: the kernels after the first are programmatic dependents of their predecessor (launch latency and
     // prologue overlap the predecessor's tail); not while per-kernel events are being recorded
     if (flags & DRA_F_NODE_SORTED) {
+        if (n_dev) return fail(ctx, DRA_E_INVAL, "DRA_F_NODE_SORTED is not supported by the sharded call");
         uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
         k_sorted_prep<<<blocks, 256, 0, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
                                                        ctx->d_sorted, d_out, n_out, err);
@@ -299,10 +312,10 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
             Prefetch pf;
             pf.p[0] = inv_src;
             pf.bytes[0] = std::min<uint32_t>(ctx->n_gpu * 16u, 1u << 20) & ~15u;
-            pf.p[1] = ctx->d_node_off; pf.bytes[1] = std::min<uint32_t>((n_node + 1) * 4u, 1u << 20) & ~15u;
+            pf.p[1] = d_node_off; pf.bytes[1] = std::min<uint32_t>((n_node + 1) * 4u, 1u << 20) & ~15u;
             pf.p[2] = ctx->d_tbl; pf.bytes[2] = 1024;
             k_bucket_small<<<1, 1024, small_smem, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
-                                                                 ctx->d_sorted, d_out, n_out, err, pf);
+                                                                 ctx->d_sorted, d_out, n_out, err, pf, n_dev);
             ctx->launches += 1;
             prof.mark(); prof.skip_to(3);
         } else {
@@ -314,11 +327,12 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
                     ctx->hist8_smem_set = (int)smem;
                 }
                 if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
-                k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank);
+                k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank, n_dev);
                 prof.mark();
                 CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 7) / 8), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
                 prof.mark();
             } else {
+                if (n_dev) return fail(ctx, DRA_E_INVAL, "sharded call: node range too wide for the CTA-wide histogram");
                 size_t smem = ((size_t)n_node + 1) * sizeof(uint16_t);
                 if (smem > 200 * 1024) return fail(ctx, DRA_E_INVAL, "n_node=%u exceeds the bucketing limit", n_node);
                 if (smem > 48 * 1024 && ctx->hist_smem_set < (int)smem) {
@@ -332,7 +346,7 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
             }
             uint32_t blocks = std::max(1u, (n_claim + 255) / 256);
             CU(launch_k(k_bucket_scatter, dim3(blocks), dim3(256), 0, ctx->stream, pdl, d_claims, n_claim, n_node, t.T, ctx->d_hist, ctx->d_rank,
-                        ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err));
+                        ctx->d_claim_off, d_out_off, ctx->d_sorted, d_out, n_out, err, n_dev));
             prof.mark();
             ctx->launches += 3;
         }
@@ -341,12 +355,24 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
     return DRA_OK;
 }
 
+// The part of the inventory a launch works on (sharded call: this rank's node range; claims carry LOCAL node
+// indices, GPU indices stay global because node_off keeps its global values) and where the claim count comes from.
+struct AllocView {
+    uint32_t node_lo = 0, n_node = 0;
+    const uint32_t* n_dev = nullptr;      // device-side claim count (the claim list was compacted on the device)
+    int have_off = -1;                    // -1: from d_out_off; else the CALLER's out_off convention (spec §1/§3)
+    bool no_pdl_first = false;
+};
+
 int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
-                    uint2* d_out, uint32_t n_out, uint32_t flags, const PeerTail* tail = nullptr, bool* tail_done = nullptr) {
+                    uint2* d_out, uint32_t n_out, uint32_t flags, const PktGather* tail = nullptr, bool* tail_done = nullptr,
+                    const AllocView* view = nullptr) {
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
     int rc = upload_table(ctx);
     if (rc) return rc;
-    const uint32_t n_node = ctx->n_node;
+    const uint32_t n_node = view ? view->n_node : ctx->n_node;
+    const uint32_t* d_node_off = ctx->d_node_off + (view ? view->node_lo : 0u);
+    const uint32_t* n_dev = view ? view->n_dev : nullptr;
     Err err = err_of(ctx);
     Prof prof(ctx);
 
@@ -354,20 +380,41 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     memset(&a, 0, sizeof a);
     a.inv_src = (flags & DRA_F_FRESH_INVENTORY) ? ctx->d_inv_pristine : ctx->d_inv_live;
     a.inv_dst = ctx->d_inv_live;
-    a.node_off = ctx->d_node_off;
+    a.node_off = d_node_off;
     a.tbl = ctx->d_tbl;
-    a.out = d_out; a.n_out = n_out; a.n_node = n_node; a.have_off = d_out_off != nullptr;
+    a.out = d_out; a.n_out = n_out; a.n_node = n_node;
+    a.have_off = (view && view->have_off >= 0) ? (uint32_t)view->have_off : (d_out_off != nullptr);
+    a.n_dev = n_dev;
     a.err = err;
     a.sel = sel_of(ctx);
 
-    const FusedPlan plan = fused_plan(ctx, n_claim, flags);
+    const FusedPlan plan = fused_plan(ctx, n_claim, flags, n_node);
     const bool fused = plan.fused, stage = plan.stage;
     const size_t fused_smem = plan.smem;
     const DirectIO dio = ctx->dio_pending;
     ctx->dio_pending = DirectIO{};
     if (dio.h_claims && !(fused && stage)) return fail(ctx, DRA_E_STATE, "direct host I/O was planned for a batch that does not take the staged single-launch kernel");
     if (fused) {
-        if (tail) { a.peer = *tail; if (tail_done) *tail_done = true; }
+        // the gather tail has every CTA wait for its peers' packets: all CTAs of the grid must be resident at once
+        bool tail_ok = tail != nullptr;
+        if (tail_ok) {
+            if (ctx->tail_cap_smem != (int)fused_smem || ctx->tail_cap_stage != (int)stage) {
+                if (fused_smem > 48 * 1024) {
+                    int& set_ = stage ? ctx->fused_smem_set_stage : ctx->fused_smem_set;
+                    if (set_ < (int)fused_smem) {
+                        if (stage) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+                        else CU(cudaFuncSetAttribute(k_fused<FUSED_NW, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+                        set_ = (int)fused_smem;
+                    }
+                }
+                int nb = 0;
+                if (stage) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, true, 1>, FUSED_NW * 32, fused_smem));
+                else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, false, 1>, FUSED_NW * 32, fused_smem));
+                ctx->tail_cap_smem = (int)fused_smem; ctx->tail_cap_stage = (int)stage; ctx->tail_cap_cta = nb * ctx->n_sm;
+            }
+            tail_ok = (int)(n_node + 1) <= ctx->tail_cap_cta;
+        }
+        if (tail_ok) { a.peer = *tail; if (tail_done) *tail_done = true; }
         // clusters of 8 CTAs + TMA multicast when the array is staged and there are enough nodes to share it
         constexpr int CLS = 8;
         // Measured (profiles/cluster_multicast_r01e.txt): multicast cuts the filter phase 4.6K -> 4.0K cycles but
@@ -424,7 +471,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
 
     static const bool no_pdl = getenv("DRA_NO_PDL") != nullptr;
     const bool pdl = !no_pdl && !ctx->profiling;
-    if ((rc = launch_sort(ctx, d_claims, n_claim, d_out_off, d_out, n_out, flags, prof, a.inv_src, pdl))) return rc;
+    if ((rc = launch_sort(ctx, d_claims, n_claim, d_out_off, d_out, n_out, flags, prof, a.inv_src, pdl, n_node, d_node_off, n_dev))) return rc;
 
     a.sorted = ctx->d_sorted;
     a.claim_off = ctx->d_claim_off;
@@ -452,12 +499,13 @@ int collect_timings(dra_ctx* ctx, int n_marks) {
 }
 
 int check_err(dra_ctx* ctx) {
-    uint32_t oor = ctx->h_err[ERR_OUT_RANGE], ns = ctx->h_err[ERR_NOT_SORTED], pt = ctx->h_err[ERR_PEER_TIMEOUT];
-    if (!oor && !ns && !pt) return DRA_OK;
+    uint32_t oor = ctx->h_err[ERR_OUT_RANGE], ns = ctx->h_err[ERR_NOT_SORTED], pt = ctx->h_err[ERR_PEER_TIMEOUT], sp = ctx->h_err[ERR_SHARD_PLAN];
+    if (!oor && !ns && !pt && !sp) return DRA_OK;
     for (uint32_t i = 0; i < ERR_WORDS; ++i) ctx->h_err[i] = 0;
     cudaMemsetAsync(ctx->d_err, 0, ERR_WORDS * sizeof(uint32_t), ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    if (pt) return fail(ctx, DRA_E_NCCL, "peer all-gather: a rank did not publish its slice in time");
+    if (sp) return fail(ctx, DRA_E_STATE, "sharded call: %u claims fell into this shard, more than the launch was laid out for; nothing was changed, call again", ctx->h_sc_counts ? ctx->h_sc_counts[0] : 0u);
+    if (pt) return fail(ctx, DRA_E_NCCL, "all-gather: a rank did not deliver its records in time (or aborted its batch)");
     if (ns) return fail(ctx, DRA_E_INVAL, "DRA_F_NODE_SORTED given but claims are not sorted by node; inventory unchanged");
     return fail(ctx, DRA_E_INVAL, "out_off/n_out: a claim's slots fall outside out[]; inventory state is undefined, reset it");
 }
@@ -519,15 +567,17 @@ void dra_ctx_destroy(dra_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->comm) { std::lock_guard<std::mutex> lk(g_nccl_mu); if (g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm); }
-    for (int r = 0; r < (int)PEER_MAX; ++r) if (c->peer_base[r] && c->peer_base[r] != c->peer_local) cudaIpcCloseMemHandle(c->peer_base[r]);
+    for (int r = 0; r < (int)PEER_MAX; ++r) if (c->peer_base[r] && c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->peer_local) cudaFree(c->peer_local);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_gbar) cudaFree(c->d_gbar);
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
-                   c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels, c->d_podrec};
+                   c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels, c->d_podrec, c->d_cursor, c->d_cclaims, c->d_coff,
+                   c->d_sc_status, c->d_sc_counts, c->d_gtable};
     for (void* p : dev) if (p) cudaFree(p);
     if (c->h_err) cudaFreeHost((void*)c->h_err);
+    if (c->h_sc_counts) cudaFreeHost((void*)c->h_sc_counts);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
@@ -682,7 +732,7 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
     // host buffer and writes the OutRecs back there — no copy-engine transfers, no graph, one cooperative launch.
     {
         static const bool no_direct = getenv("DRA_NO_DIRECT") != nullptr || getenv("DRA_CLUSTER") != nullptr;   // (the cluster experiment has no ingest)
-        const FusedPlan plan = fused_plan(ctx, n_claim, flags);
+        const FusedPlan plan = fused_plan(ctx, n_claim, flags, ctx->n_node);
         bool ok = !no_direct && !(ctx->cfg_flags & DRA_CFG_NO_DIRECT) && ctx->coop_ok && plan.fused && plan.stage && n_claim && rb &&
                   !ctx->profiling && ((uintptr_t)src_c & 15) == 0 && ((uintptr_t)dst_o & 15) == 0 &&
                   (!src_o || ((uintptr_t)src_o & 3) == 0);
@@ -903,7 +953,7 @@ int dra_allocate_pods_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t 
     static const bool no_pdl = getenv("DRA_NO_PDL") != nullptr;
     const bool pdl = !no_pdl && !ctx->profiling;
     const uint4* inv_src = (flags & DRA_F_FRESH_INVENTORY) ? ctx->d_inv_pristine : ctx->d_inv_live;
-    if ((rc = launch_sort(ctx, ctx->d_podrec, n_pod, nullptr, nullptr, 0, 0, prof, inv_src, false))) return rc;
+    if ((rc = launch_sort(ctx, ctx->d_podrec, n_pod, nullptr, nullptr, 0, 0, prof, inv_src, false, ctx->n_node, ctx->d_node_off))) return rc;
     PodArgs a; memset(&a, 0, sizeof a);
     a.claims = ctx->d_claims; a.out_off = d_oo; a.out = d_out;
     a.sorted = ctx->d_sorted; a.claim_off = ctx->d_claim_off;
@@ -978,99 +1028,162 @@ int dra_comm_init(dra_ctx* ctx, const void* id128, int rank, int world) {
     return DRA_OK;
 }
 
-int dra_peer_export(dra_ctx* ctx, uint32_t n_per_rank, void* handle64) {
-    if (!ctx) return DRA_E_INVAL;
-    if (!n_per_rank) { ctx->peer_ready = false; return DRA_OK; }          // switch the peer path off (NCCL again)
-    if (!handle64) return DRA_E_INVAL;
-    if (!ctx->comm) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called");
+namespace {
+
+// (Re)allocates this rank's gather buffer:  [table x2][staging x2: world slices of cap packets][headers x2]
+int peer_setup(dra_ctx* ctx, uint32_t form, uint32_t n_per, uint32_t tab_len, uint32_t cap) {
     if (ctx->world > (int)PEER_MAX) return fail(ctx, DRA_E_INVAL, "world %d > %u", ctx->world, PEER_MAX);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->peer_ready = false;
+    for (int r = 0; r < (int)PEER_MAX; ++r) {
+        if (ctx->peer_base[r] && ctx->peer_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_base[r]);
+        ctx->peer_base[r] = nullptr; ctx->peer_ipc[r] = false;
+    }
     if (ctx->peer_local) { CU(cudaFree(ctx->peer_local)); ctx->peer_local = nullptr; }
-    const uint32_t n_per = (n_per_rank + 1u) & ~1u;                       // slices are copied as uint4
-    const size_t data = (size_t)2 * ctx->world * n_per * 8;
-    ctx->peer_flag_off = (data + 255) & ~(size_t)255;
-    ctx->peer_bytes = ctx->peer_flag_off + 256;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    for (int p = 0; p < 2; ++p) ctx->off_table[p] = take((size_t)tab_len * 8 + 16);
+    for (int p = 0; p < 2; ++p) ctx->off_stage[p] = take((size_t)ctx->world * cap * 16);
+    for (int p = 0; p < 2; ++p) ctx->off_hdr[p] = take((size_t)ctx->world * 16);
+    ctx->peer_bytes = off;
     CU(cudaMalloc((void**)&ctx->peer_local, ctx->peer_bytes));
     CU(cudaMemset(ctx->peer_local, 0, ctx->peer_bytes));
-    if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemset(ctx->d_ticket, 0, 64)); }
+    if (!ctx->d_cursor) CU(cudaMalloc((void**)&ctx->d_cursor, 64));
+    CU(cudaMemset(ctx->d_cursor, 0, 64));
+    ctx->peer_form = form; ctx->peer_n_per = n_per; ctx->peer_tab_len = tab_len; ctx->peer_cap = cap; ctx->peer_epoch = 0;
+    if (const char* e = getenv("DRA_PEER_TIMEOUT_MS")) ctx->peer_spin = std::max(1ll, atoll(e)) * 1900000ll;
+    ctx->gather_table = nullptr;
+    ctx->state_epoch++;
+    return DRA_OK;
+}
+
+PktGather make_gather(dra_ctx* ctx, uint32_t epoch, uint32_t slot_base, uint32_t n_per, uint32_t count, const uint32_t* count_dev) {
+    PktGather g; memset(&g, 0, sizeof g);
+    const uint32_t par = epoch & 1u;
+    for (int r = 0; r < ctx->world; ++r) {
+        g.stage[r] = (uint4*)(ctx->peer_base[r] + ctx->off_stage[par]) + (size_t)ctx->rank * ctx->peer_cap;
+        g.hdr[r] = (uint4*)(ctx->peer_base[r] + ctx->off_hdr[par]) + ctx->rank;
+    }
+    g.my_stage = (const uint4*)(ctx->peer_local + ctx->off_stage[par]);
+    g.my_hdr = (const uint4*)(ctx->peer_local + ctx->off_hdr[par]);
+    g.table = (uint2*)(ctx->peer_local + ctx->off_table[par]);
+    g.cursor = ctx->d_cursor;
+    g.world = ctx->world; g.rank = ctx->rank; g.cap = ctx->peer_cap; g.epoch = epoch; g.parity = par;
+    g.slot_base = slot_base; g.n_per = n_per; g.count = count; g.count_dev = count_dev; g.spin_limit = ctx->peer_spin;
+    return g;
+}
+
+int launch_gather(dra_ctx* ctx, const PktGather& g, const uint4* d_claims, uint32_t n_claim, const uint32_t* n_dev,
+                  const uint32_t* d_out_off, uint32_t n_out, uint32_t have_off, uint32_t n_node) {
+    const uint32_t blocks = std::max(1u, std::min((uint32_t)ctx->n_sm * 2u, (std::max(n_claim, g.world * g.cap / 4u) + 255u) / 256u));
+    k_pkt_gather<<<blocks, 256, 0, ctx->stream>>>(g, d_claims, n_claim, n_dev, d_out_off, n_out, have_off, n_node, err_of(ctx));
+    ctx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "k_pkt_gather: %s", cudaGetErrorString(e));
+    return DRA_OK;
+}
+
+}  // namespace
+
+int dra_peer_export(dra_ctx* ctx, uint32_t n_per_rank, void* handle64) {
+    if (!ctx) return DRA_E_INVAL;
+    if (!n_per_rank) { ctx->peer_ready = false; return DRA_OK; }          // switch the peer path off (NCCL again)
+    if (!handle64) return DRA_E_INVAL;
+    int rc = peer_setup(ctx, 1, n_per_rank, (uint32_t)ctx->world * n_per_rank, n_per_rank);
+    if (rc) return rc;
     cudaIpcMemHandle_t h;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     CU(cudaIpcGetMemHandle(&h, ctx->peer_local));
     memcpy(handle64, &h, 64);
-    ctx->peer_n_per = n_per; ctx->peer_epoch = 0;
+    return DRA_OK;
+}
+
+int dra_shard_export(dra_ctx* ctx, uint32_t n_out_max, uint32_t cap_per_rank, void* handle64) {
+    if (!ctx || !n_out_max) return DRA_E_INVAL;
+    if (n_out_max > (1u << 26)) return fail(ctx, DRA_E_INVAL, "n_out_max %u exceeds 2^26", n_out_max);
+    int rc = peer_setup(ctx, 2, 0, n_out_max, cap_per_rank ? std::min(cap_per_rank, n_out_max) : n_out_max);
+    if (rc) return rc;
+    if (handle64) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ctx->peer_local));
+        memcpy(handle64, &h, 64);
+    }
     return DRA_OK;
 }
 
 int dra_peer_import(dra_ctx* ctx, const void* handles) {
     if (!ctx || !handles) return DRA_E_INVAL;
-    if (!ctx->peer_local) return fail(ctx, DRA_E_STATE, "dra_peer_export has not been called");
+    if (!ctx->peer_local) return fail(ctx, DRA_E_STATE, "dra_peer_export / dra_shard_export has not been called");
     CU(cudaSetDevice(ctx->device));
     for (int r = 0; r < ctx->world; ++r) {
-        if (r == ctx->rank) { ctx->peer_base[r] = ctx->peer_local; continue; }
+        if (r == ctx->rank) { ctx->peer_base[r] = ctx->peer_local; ctx->peer_ipc[r] = false; continue; }
         cudaIpcMemHandle_t h; memcpy(&h, (const uint8_t*)handles + (size_t)r * 64, 64);
         void* p = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, DRA_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e)); }
-        ctx->peer_base[r] = (uint8_t*)p;
+        ctx->peer_base[r] = (uint8_t*)p; ctx->peer_ipc[r] = true;
     }
     ctx->peer_ready = true;
+    return DRA_OK;
+}
+
+int dra_peer_import_local(dra_ctx* ctx, dra_ctx* const* ctxs) {
+    if (!ctx || !ctxs) return DRA_E_INVAL;
+    if (!ctx->peer_local) return fail(ctx, DRA_E_STATE, "dra_peer_export / dra_shard_export has not been called");
+    CU(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->world; ++r) {
+        dra_ctx* o = ctxs[r];
+        if (!o || !o->peer_local || o->world != ctx->world || o->rank != r || o->peer_form != ctx->peer_form ||
+            o->peer_cap != ctx->peer_cap || o->peer_tab_len != ctx->peer_tab_len)
+            return fail(ctx, DRA_E_INVAL, "dra_peer_import_local: context %d is not set up like this one", r);
+        if (o->device != ctx->device) {
+            int ok = 0; CU(cudaDeviceCanAccessPeer(&ok, ctx->device, o->device));
+            if (!ok) return fail(ctx, DRA_E_CUDA, "no peer access from device %d to %d", ctx->device, o->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, DRA_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+        }
+        ctx->peer_base[r] = o->peer_local; ctx->peer_ipc[r] = false;
+    }
+    ctx->peer_ready = true;
+    return DRA_OK;
+}
+
+int dra_comm_init_local(dra_ctx* ctx, int rank, int world) {
+    if (!ctx || world < 1 || world > (int)PEER_MAX || rank < 0 || rank >= world) return DRA_E_INVAL;
+    ctx->rank = rank; ctx->world = world;
     return DRA_OK;
 }
 
 int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                                      dra_out_rec* d_out_all, uint32_t n_out, uint32_t n_per_rank, uint32_t flags) {
     if (!ctx || (n_claim && !d_claims)) return DRA_E_INVAL;
-    if (!ctx->comm) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called");
+    if (!ctx->comm && !ctx->peer_ready) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called");
     if (!d_out_all && !ctx->peer_ready) return fail(ctx, DRA_E_INVAL, "d_out_all may be NULL only with the peer all-gather set up");
     if (n_out > n_per_rank) return fail(ctx, DRA_E_INVAL, "n_out %u > n_per_rank %u", n_out, n_per_rank);
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_batch(ctx, n_claim, n_out, false);
     if (rc) return rc;
 
-    if (ctx->peer_ready && ((n_per_rank + 1u) & ~1u) == ctx->peer_n_per && (n_per_rank & 1u) == 0) {
-        // ---- peer-memory all-gather: kernel writes its slice, push kernel stores it into every peer ----
-        const uint32_t n_per = ctx->peer_n_per;
+    if (ctx->peer_ready && ctx->peer_form == 1 && n_per_rank == ctx->peer_n_per) {
+        // ---- packet all-gather over NVLink: rides in the tail of the fused kernel, or runs as its own kernel ----
         ctx->peer_epoch += 1;
-        PeerArgs pa; memset(&pa, 0, sizeof pa);
-        for (int r = 0; r < ctx->world; ++r) {
-            pa.buf[r] = (uint4*)ctx->peer_base[r];
-            pa.flags[r] = (uint32_t*)(ctx->peer_base[r] + ctx->peer_flag_off);
-        }
-        pa.ticket = ctx->d_ticket; pa.world = ctx->world; pa.rank = ctx->rank; pa.n_per16 = n_per / 2;
-        pa.epoch = ctx->peer_epoch; pa.parity = ctx->peer_epoch & 1u; pa.err = err_of(ctx);
-        dra_out_rec* mine = (dra_out_rec*)ctx->peer_local + ((size_t)pa.parity * ctx->world + ctx->rank) * n_per;
-        if (n_per > n_out) CU(cudaMemsetAsync(mine + n_out, 0, (size_t)(n_per - n_out) * 8, ctx->stream));
-        // preferred: the collective rides in the tail of the fused kernel (no extra launch)
-        PeerTail tail; memset(&tail, 0, sizeof tail);
-        for (int r = 0; r < ctx->world; ++r) {
-            tail.peer_out[r] = (uint2*)((dra_out_rec*)ctx->peer_base[r] + ((size_t)pa.parity * ctx->world + ctx->rank) * n_per);
-            tail.flags[r] = pa.flags[r];
-        }
-        tail.ticket = ctx->d_ticket; tail.world = ctx->world; tail.rank = ctx->rank; tail.n_per16 = n_per / 2; tail.epoch = pa.epoch;
+        const PktGather g = make_gather(ctx, ctx->peer_epoch, (uint32_t)ctx->rank * n_per_rank, n_per_rank, n_out, nullptr);
+        uint2* mine = g.table + g.slot_base;
         bool tail_done = false;
-        rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags, &tail, &tail_done);
+        rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, mine, n_out, flags, &g, &tail_done);
         if (rc) return rc;
-        const dra_out_rec* table = (const dra_out_rec*)ctx->peer_local + (size_t)pa.parity * ctx->world * n_per;
-        ctx->gather_table = table; ctx->gather_n_per = n_per;
-        if (!tail_done) {                                   // sort path: separate push / wait kernels
-            const uint32_t push_blocks = std::max(1u, std::min(32u, (pa.n_per16 + 255) / 256));
-            k_peer_push<<<push_blocks, 256, 0, ctx->stream>>>(pa);
-            const uint32_t wait_blocks = std::max(1u, std::min(64u, (pa.n_per16 * ctx->world + 255) / 256));
-            k_peer_wait<<<wait_blocks, 256, 0, ctx->stream>>>(pa, (uint4*)d_out_all);
-            ctx->launches += 2;
-        } else if (d_out_all) {                             // caller wants its own copy: one D2D copy node
-            CU(cudaMemcpyAsync(d_out_all, table, (size_t)ctx->world * n_per * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        }
+        if (!tail_done && (rc = launch_gather(ctx, g, (const uint4*)d_claims, n_claim, nullptr, d_out_off, n_out, d_out_off != nullptr, ctx->n_node))) return rc;
+        ctx->gather_table = (const dra_out_rec*)g.table; ctx->gather_n_per = n_per_rank; ctx->gather_len = 0;
+        if (d_out_all) CU(cudaMemcpyAsync(d_out_all, g.table, (size_t)ctx->world * n_per_rank * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (ctx->profiling && !tail_done) { cudaEventRecord(ctx->ev[5], ctx->stream); ctx->ev_mask |= 1u << 5; }
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "peer all-gather launch: %s", cudaGetErrorString(e));
         return DRA_OK;
     }
 
+    if (!ctx->comm) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called (NCCL path)");
     if (!d_out_all) return fail(ctx, DRA_E_INVAL, "d_out_all is required on the NCCL path");
-    ctx->gather_table = d_out_all; ctx->gather_n_per = n_per_rank;
+    ctx->gather_table = d_out_all; ctx->gather_n_per = n_per_rank; ctx->gather_len = 0;
     dra_out_rec* mine = d_out_all + (size_t)ctx->rank * n_per_rank;
     if (n_per_rank > n_out) CU(cudaMemsetAsync(mine + n_out, 0, (size_t)(n_per_rank - n_out) * 8, ctx->stream));
     rc = launch_allocate(ctx, (const uint4*)d_claims, n_claim, d_out_off, (uint2*)mine, n_out, flags);
@@ -1079,6 +1192,94 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     ncclResult_t r = g_nccl.AllGather(mine, d_out_all, (size_t)n_per_rank * 8, ncclUint8, ctx->comm, ctx->stream);
     if (r != ncclSuccess) return fail(ctx, DRA_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     if (ctx->profiling) { cudaEventRecord(ctx->ev[5], ctx->stream); ctx->ev_mask |= 1u << 5; }
+    return DRA_OK;
+}
+
+// ---- sharded global batch -------------------------------------------------------------------------------
+
+int dra_set_shard(dra_ctx* ctx, uint32_t node_lo, uint32_t node_hi, int take_stray) {
+    if (!ctx) return DRA_E_INVAL;
+    if (node_lo > node_hi || node_hi > ctx->n_node) return fail(ctx, DRA_E_INVAL, "shard [%u, %u) outside the inventory's %u nodes", node_lo, node_hi, ctx->n_node);
+    ctx->shard_on = true; ctx->shard_lo = node_lo; ctx->shard_hi = node_hi; ctx->shard_stray = take_stray ? 1u : 0u;
+    ctx->state_epoch++;
+    return DRA_OK;
+}
+
+int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
+                                     uint32_t n_out, uint32_t flags) {
+    if (!ctx || (n_claim && !d_claims)) return DRA_E_INVAL;
+    if (!ctx->shard_on) return fail(ctx, DRA_E_STATE, "dra_set_shard has not been called");
+    if (flags & ~DRA_F_FRESH_INVENTORY) return fail(ctx, DRA_E_INVAL, "dra_allocate_batch_global_device: unsupported flags 0x%x", flags);
+    if (n_claim > (1u << 26) || n_out > (1u << 26)) return fail(ctx, DRA_E_INVAL, "batch too large for the sharded call (2^26)");
+    if (!d_out_off && n_out < n_claim) return fail(ctx, DRA_E_INVAL, "n_out %u < n_claim %u without out_off", n_out, n_claim);
+    const bool gather = ctx->world > 1;
+    if (gather && !(ctx->peer_ready && ctx->peer_form == 2)) return fail(ctx, DRA_E_STATE, "dra_shard_export + dra_peer_import have not been called");
+    if (gather && n_out > ctx->peer_tab_len) return fail(ctx, DRA_E_INVAL, "n_out %u exceeds the exported table (%u)", n_out, ctx->peer_tab_len);
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n_local_node = ctx->shard_hi - ctx->shard_lo;
+    // plan from the previous call's count (first call: an even split), with slack; the buffers always hold n_claim
+    uint32_t expect = ctx->h_sc_counts && ctx->h_sc_counts[2] == 1u ? ctx->h_sc_counts[0]
+                                                                    : (uint32_t)((uint64_t)n_claim / (uint32_t)std::max(1, ctx->world));
+    uint32_t cap = std::min<uint64_t>(n_claim, (uint64_t)expect + expect / 10 + 128);
+    FusedPlan plan = fused_plan(ctx, cap, flags, n_local_node);
+    if (!plan.fused) cap = n_claim;                           // sort path: no layout depends on the count
+    int rc = ensure_batch(ctx, std::max(cap, 1u), n_out, false);
+    if (rc) return rc;
+    if ((size_t)n_claim + 64 > ctx->cap_cclaims) {
+        const size_t ncap = (size_t)n_claim + n_claim / 4 + 64;
+        if ((rc = grow_nc(ctx, ctx->d_cclaims, 0, ncap))) return rc;
+        if ((rc = grow_nc(ctx, ctx->d_coff, 0, ncap))) return rc;
+        ctx->cap_cclaims = ncap;
+    }
+    const uint32_t n_tiles = std::max(1u, (n_claim + SC_TILE - 1) / SC_TILE);
+    if ((size_t)n_tiles + 8 > ctx->cap_sc_status) {
+        const size_t ncap = (size_t)n_tiles * 2 + 64;
+        if ((rc = grow_nc(ctx, ctx->d_sc_status, 0, ncap))) return rc;
+        CU(cudaMemsetAsync(ctx->d_sc_status, 0, ncap * 8, ctx->stream));
+        ctx->cap_sc_status = ncap;
+    }
+    if (!ctx->d_sc_counts) {
+        CU(cudaMalloc((void**)&ctx->d_sc_counts, 64)); CU(cudaMemsetAsync(ctx->d_sc_counts, 0, 64, ctx->stream));
+        void* hp = nullptr;
+        CU(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+        memset(hp, 0, 64);
+        ctx->h_sc_counts = (volatile uint32_t*)hp;
+        CU(cudaHostGetDevicePointer((void**)&ctx->h_sc_counts_dev, hp, 0));
+    }
+    if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
+    // result table
+    uint2* table = nullptr; PktGather g; memset(&g, 0, sizeof g);
+    if (gather) {
+        ctx->peer_epoch += 1;
+        g = make_gather(ctx, ctx->peer_epoch, 0, 0, 0, ctx->d_sc_counts + 1);
+        table = g.table;
+    } else {
+        if ((size_t)n_out + 16 > ctx->cap_gtable) {
+            const size_t ncap = (size_t)n_out + n_out / 4 + 64;
+            if ((rc = grow_nc(ctx, ctx->d_gtable, 0, ncap))) return rc;
+            ctx->cap_gtable = ncap;
+        }
+        table = ctx->d_gtable;
+    }
+    // 1. this rank's claims, compacted in input order, node indices local to the shard
+    ctx->shard_epoch += 1;
+    ShardArgs sa; memset(&sa, 0, sizeof sa);
+    sa.claims = (const uint4*)d_claims; sa.n_claim = n_claim; sa.out_off = d_out_off;
+    sa.node_lo = ctx->shard_lo; sa.node_hi = ctx->shard_hi; sa.n_node_global = ctx->n_node; sa.take_stray = ctx->shard_stray;
+    sa.have_off = d_out_off != nullptr;
+    sa.cclaims = ctx->d_cclaims; sa.coff = ctx->d_coff; sa.cap = (uint32_t)std::min<size_t>(ctx->cap_cclaims, 0xFFFFFFFFu);
+    sa.status = ctx->d_sc_status; sa.ticket = ctx->d_ticket + 4; sa.n_tiles = n_tiles; sa.epoch = ctx->shard_epoch;
+    sa.counts = ctx->d_sc_counts; sa.h_counts = ctx->h_sc_counts_dev; sa.err = err_of(ctx);
+    k_shard_compact<<<n_tiles, 256, 0, ctx->stream>>>(sa);
+    ctx->launches += 1;
+    ctx->h_sc_counts[2] = 1u;                                 // (host-side note: counts of a call exist from now on)
+    // 2. the usual chain on the shard's view of the inventory, results at the claims' GLOBAL slots
+    AllocView view; view.node_lo = ctx->shard_lo; view.n_node = n_local_node; view.n_dev = ctx->d_sc_counts; view.have_off = d_out_off != nullptr;
+    bool tail_done = false;
+    rc = launch_allocate(ctx, ctx->d_cclaims, cap, ctx->d_coff, table, n_out, flags, gather ? &g : nullptr, &tail_done, &view);
+    if (rc) return rc;
+    if (gather && !tail_done && (rc = launch_gather(ctx, g, ctx->d_cclaims, cap, ctx->d_sc_counts, ctx->d_coff, n_out, d_out_off != nullptr, n_local_node))) return rc;
+    ctx->gather_table = (const dra_out_rec*)table; ctx->gather_n_per = n_out; ctx->gather_len = n_out;
     return DRA_OK;
 }
 
@@ -1093,7 +1294,7 @@ int dra_gather_table(dra_ctx* ctx, const dra_out_rec** d_table, uint32_t* n_per_
 int dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec) {
     if (!ctx || !out_all) return DRA_E_INVAL;
     if (!ctx->gather_table) return fail(ctx, DRA_E_STATE, "no gather has run");
-    if (n_rec > (uint32_t)ctx->world * ctx->gather_n_per) return fail(ctx, DRA_E_INVAL, "n_rec %u exceeds the table", n_rec);
+    if (n_rec > (ctx->gather_len ? ctx->gather_len : (uint32_t)ctx->world * ctx->gather_n_per)) return fail(ctx, DRA_E_INVAL, "n_rec %u exceeds the table", n_rec);
     CU(cudaSetDevice(ctx->device));
     const size_t rb = (size_t)n_rec * 8;
     const bool direct = is_pinned(out_all, rb);

@@ -30,7 +30,8 @@ constexpr uint32_t RING = 4;          // ring slots per warp
 constexpr uint32_t ERR_OUT_RANGE = 1u;    // index into the error-flag words
 constexpr uint32_t ERR_NOT_SORTED = 2u;
 constexpr uint32_t ERR_PEER_TIMEOUT = 3u;
-constexpr uint32_t ERR_WORDS = 4u;
+constexpr uint32_t ERR_SHARD_PLAN = 4u;      // sharded call: more claims fell into this shard than the launch was laid out for
+constexpr uint32_t ERR_WORDS = 8u;
 
 // Error flags: `dev` (device memory) gates later kernels of the same batch, `host` (mapped pinned
 // memory) is what the host reads after the stream drains.  Idempotent plain stores, errors are rare.
@@ -469,9 +470,10 @@ k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node,
 constexpr uint32_t H8_TILE = 2048;
 __global__ void __launch_bounds__(256)
 k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
-               uint32_t* __restrict__ hist, uint16_t* __restrict__ rank) {
+               uint32_t* __restrict__ hist, uint16_t* __restrict__ rank, const uint32_t* __restrict__ n_dev) {
     extern __shared__ uint16_t cnt8[];                              // [8][nbp]
     pdl_trigger();
+    if (n_dev) n_claim = min(n_claim, __ldcg(n_dev));               // sharded call: compacted on the device
     const uint32_t nb = n_node + 1, nbp = (nb + 1) & ~1u;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nbits = 32u - (uint32_t)__clz(n_node);
@@ -586,9 +588,10 @@ __global__ void __launch_bounds__(256)
 k_bucket_scatter(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node, uint32_t T,
                  const uint32_t* __restrict__ hist, const uint16_t* __restrict__ rank,
                  const uint32_t* __restrict__ claim_off, const uint32_t* __restrict__ out_off,
-                 uint4* __restrict__ sorted, uint2* __restrict__ out, uint32_t n_out, Err err) {
+                 uint4* __restrict__ sorted, uint2* __restrict__ out, uint32_t n_out, Err err, const uint32_t* __restrict__ n_dev) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_claim) return;
+    if (n_dev) n_claim = min(n_claim, __ldcg(n_dev));
+    if (i >= n_claim) { pdl_trigger(); return; }
     uint4 c = __ldg(&claims[i]);
     const uint32_t dst = out_off ? __ldg(&out_off[i]) : i;
     pdl_trigger(); pdl_wait();                             // the inputs above do not come from the chain
@@ -621,9 +624,11 @@ constexpr int BS_CHUNK = 16;
 __global__ void __launch_bounds__(1024)
 k_bucket_small(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
                const uint32_t* __restrict__ out_off, uint32_t* __restrict__ claim_off,
-               uint4* __restrict__ sorted, uint2* __restrict__ out, uint32_t n_out, Err err, Prefetch pf) {
+               uint4* __restrict__ sorted, uint2* __restrict__ out, uint32_t n_out, Err err, Prefetch pf,
+               const uint32_t* __restrict__ n_dev) {
     extern __shared__ uint32_t sm_u32[];
     pdl_trigger();
+    if (n_dev) n_claim = min(n_claim, __ldcg(n_dev));
     const uint32_t nb = n_node + 1, nbp = (nb + 1) & ~1u;
     uint32_t* off = sm_u32;                                        // [nbp]
     uint16_t* cnt = reinterpret_cast<uint16_t*>(off + nbp);        // [32][nbp]
@@ -771,17 +776,222 @@ k_sorted_prep(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_nod
 }
 
 // ====================================================================================================
+// sharded global batch: every rank reads the WHOLE claim array and keeps the claims of its own node range
+// ====================================================================================================
+// (pool = node: vendor/k8s.io/dynamic-resource-allocation/kubeletplugin/draplugin.go:427-435 — nodes are sharded whole.)
+// Stable compaction in one pass: tiles of 2048 claims, taken by ticket; a tile's prefix comes from a decoupled
+// look-back over the earlier tiles' status words (state | epoch | claims | slots in ONE 64-bit word, so no fence).
+// Kept claims are rewritten with the node index LOCAL to the shard; claims naming no node go to the rank with
+// take_stray set (they come back INVALID, spec §3).  coff[j] = first GLOBAL OutRec slot of kept claim j.
+constexpr uint32_t SC_TILE = 2048;
+struct ShardArgs {
+    const uint4* claims; uint32_t n_claim; const uint32_t* out_off;
+    uint32_t node_lo, node_hi, n_node_global, take_stray, have_off;
+    uint4* cclaims; uint32_t* coff; uint32_t cap;
+    unsigned long long* status; uint32_t* ticket; uint32_t n_tiles, epoch;
+    uint32_t* counts;                 // [0] claims kept, [1] their OutRec slots
+    volatile uint32_t* h_counts;      // the same, mapped host memory (plan hint for the next call)
+    Err err;
+};
+__device__ __forceinline__ unsigned long long sc_pack(uint32_t epoch, uint32_t state, uint32_t c, uint32_t s_) {
+    return ((unsigned long long)state << 62) | ((unsigned long long)(epoch & 0x3FFu) << 52) | ((unsigned long long)(c & 0x3FFFFFFu) << 26) | (s_ & 0x3FFFFFFu);
+}
+__global__ void __launch_bounds__(256)
+k_shard_compact(const ShardArgs a) {
+    __shared__ uint32_t tile_s, rowc[64], rows[64], pre_c, pre_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ltm = lanemask_lt();
+    if (tid == 0) {
+        const uint32_t t = atomicAdd(a.ticket, 1u);
+        if (t == a.n_tiles - 1) *a.ticket = 0;                    // the last ticket of this launch: ready for the next
+        tile_s = t;
+    }
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const uint32_t w0 = tile * SC_TILE + wid * 256;
+    uint4 c[8]; uint32_t keepm = 0, rk[8];
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) { const uint32_t i = w0 + r * 32 + lane; c[r] = i < a.n_claim ? __ldg(&a.claims[i]) : make_uint4(0, 0xFFFFFFFDu, 0, 0); }
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = w0 + r * 32 + lane, node = c[r].y;
+        const bool stray = node >= a.n_node_global;
+        const bool keep = i < a.n_claim && (stray ? a.take_stray != 0 : (node >= a.node_lo && node < a.node_hi));
+        const uint32_t kind = c[r].x & 0xFFu, count = c[r].x >> 16;
+        const uint32_t sl = !keep ? 0u : ((kind == DRA_KIND_GPU && !stray && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u);
+        const uint32_t b = __ballot_sync(FULLMASK, keep);
+        rk[r] = (uint32_t)__popc(b & ltm);
+        keepm |= keep ? (1u << r) : 0u;
+        const uint32_t ss = __reduce_add_sync(FULLMASK, sl);
+        if (lane == 0) { rowc[wid * 8 + r] = (uint32_t)__popc(b); rows[wid * 8 + r] = ss; }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        // exclusive scan of the 64 row counts (two per lane), tile totals
+        const uint32_t c0 = rowc[2 * lane], c1 = rowc[2 * lane + 1], s0 = rows[2 * lane], s1 = rows[2 * lane + 1];
+        uint32_t xc = c0 + c1, xs = s0 + s1;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t yc = __shfl_up_sync(FULLMASK, xc, d), ys = __shfl_up_sync(FULLMASK, xs, d);
+            if (lane >= (uint32_t)d) { xc += yc; xs += ys; }
+        }
+        const uint32_t tc = __shfl_sync(FULLMASK, xc, 31), ts = __shfl_sync(FULLMASK, xs, 31);
+        rowc[2 * lane] = xc - c0 - c1; rowc[2 * lane + 1] = xc - c1;
+        // publish the aggregate, look back for the prefix, publish the inclusive prefix
+        unsigned long long* st = a.status;
+        if (lane == 0) atomicExch(&st[tile], sc_pack(a.epoch, tile == 0 ? 2u : 1u, tc, ts));
+        uint32_t ec = 0, es = 0;
+        int look = (int)tile - 1;
+        const long long t0 = clock64();
+        bool dead = false;
+        while (look >= 0 && !dead) {
+            const int idx = look - (int)lane;
+            unsigned long long v = 0; bool ready;
+            do {
+                if (idx >= 0) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(st + idx) : "memory");
+                ready = idx < 0 || (((v >> 52) & 0x3FFu) == (a.epoch & 0x3FFu) && (v >> 62) != 0);
+                if (clock64() - t0 > 2000000000ll) dead = true;
+            } while (!__all_sync(FULLMASK, ready || dead));
+            const uint32_t m2 = __ballot_sync(FULLMASK, idx < 0 || (v >> 62) == 2u);
+            const uint32_t upto = m2 ? (uint32_t)__ffs(m2) - 1u : 31u;
+            const bool inc = idx >= 0 && lane <= upto;
+            ec += __reduce_add_sync(FULLMASK, inc ? (uint32_t)((v >> 26) & 0x3FFFFFFu) : 0u);
+            es += __reduce_add_sync(FULLMASK, inc ? (uint32_t)(v & 0x3FFFFFFu) : 0u);
+            if (m2) break;
+            look -= 32;
+        }
+        if (dead && lane == 0) a.err.set(ERR_PEER_TIMEOUT);
+        if (lane == 0) {
+            if (tile) atomicExch(&st[tile], sc_pack(a.epoch, 2u, ec + tc, es + ts));
+            pre_c = ec; pre_s = es;
+            if (tile == a.n_tiles - 1) {
+                a.counts[0] = ec + tc; a.counts[1] = es + ts;
+                a.h_counts[0] = ec + tc; a.h_counts[1] = es + ts;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t base = pre_c;
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (!((keepm >> r) & 1u)) continue;
+        const uint32_t i = w0 + r * 32 + lane;
+        const uint32_t pos = base + rowc[wid * 8 + r] + rk[r];
+        if (pos >= a.cap) { a.err.set(ERR_OUT_RANGE); continue; }
+        uint4 v = c[r];
+        v.y = v.y >= a.n_node_global ? 0xFFFFFFFFu : v.y - a.node_lo;
+        a.cclaims[pos] = v;
+        a.coff[pos] = a.out_off ? __ldg(&a.out_off[i]) : i;
+    }
+}
+
+// ====================================================================================================
 // pack: first-fit per node
 // ====================================================================================================
 
-// Tail of k_fused in multi-GPU mode: the path's one collective done with NVLink P2P stores, no extra launch.
+// ---- the path's one collective: all-gather of OutRecs as self-validating 16-byte packets over NVLink ----------------
+// Measured on 8 B200s (profiles/peer_bench_r02.txt): a flag round trip between two GPUs is 4.9 us, a system fence
+// after remote stores costs a full round trip, and 70k scattered 8-byte remote stores (what r01's tail issued at
+// N=8) take ~13 us to drain.  So: no fence, no flag, no ticket.  Every OutRec travels as ONE 16-byte store
+//   { gpu, meta | tag(epoch) in meta's spare bits, table slot, epoch }
+// into a staging slice of the receiver (each 8-byte half carries its own validity tag, so even a torn read is
+// caught); a CTA reserves a CONTIGUOUS range of its rank's slice with one atomicAdd, so a node's ~80 packets leave as
+// ~10 full 128-byte lines instead of 80 sector writes — the slot rides in the packet, order does not matter.
+// Receivers poll their own (local) staging memory and scatter the records into the result table.  Latency after the
+// slowest CTA of any rank: one NVLink hop (2.5 us) + one L2 probe.
 constexpr uint32_t PEER_MAX = 16;
-struct PeerTail {
-    uint2* peer_out[PEER_MAX];    // this rank's slice inside every rank's gather buffer (peer_out[rank] == out)
-    uint32_t* flags[PEER_MAX];    // every rank's flag array (one word per source rank)
-    uint32_t* ticket;
-    uint32_t world, rank, n_per16, epoch;
+constexpr uint32_t PKT_CLEAN = ~(0xF0u | 0xE000u | 0xF8000000u);      // meta bits that are always zero (start <= 15, size <= 16, status <= 7)
+struct PktGather {
+    uint4* stage[PEER_MAX];       // stage[p]: THIS rank's slice inside peer p's staging area (parity applied)
+    uint4* hdr[PEER_MAX];         // hdr[p]: this rank's header slot at peer p
+    const uint4* my_stage;        // this rank's own staging area: slice r at my_stage + r * cap
+    const uint4* my_hdr;          // [world]
+    uint2* table;                 // this rank's result table (parity applied)
+    uint32_t* cursor;             // [2] reservation cursors, one per parity
+    uint32_t world, rank, cap, epoch, parity;
+    uint32_t slot_base;           // table index of this rank's local slot 0 (slice form: rank * n_per; global form: 0)
+    uint32_t n_per;               // slice form: every rank's padding [count_r, n_per) is zeroed by the receiver; 0: global slots
+    uint32_t count;               // packets (OutRec slots) this rank sends, when the host knows it ...
+    const uint32_t* count_dev;    // ... else it is read here
+    long long spin_limit;         // clock cycles before a missing packet becomes ERR_PEER_TIMEOUT (never a hang)
 };
+
+__device__ __forceinline__ uint32_t pkt_tag(uint32_t meta, uint32_t epoch) {
+    const uint32_t t = epoch & 0xFFFu;
+    return meta | ((t & 0xFu) << 4) | (((t >> 4) & 7u) << 13) | (((t >> 7) & 0x1Fu) << 27);
+}
+__device__ __forceinline__ void pkt_store(uint4* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 pkt_load(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// header of this rank to every peer: how many packets it has sent (0xFFFFFFFF: it gave up).  One thread per peer.
+// Sent by the LAST sending CTA with the final value of the reservation cursor, so the count is exactly what went out
+// even when the caller's out_off leaves gaps.
+__device__ __forceinline__ void pkt_send_header(const PktGather& g, uint32_t p, uint32_t n) {
+    if (p >= g.world || p == g.rank) return;
+    pkt_store(g.hdr[p], n, n ^ g.epoch ^ 0xA5A5A5A5u, 0u, g.epoch);
+}
+// CTA-collective: called by every CTA of the grid once its packets are out; the last one publishes the count
+__device__ __forceinline__ void pkt_finish_send(const PktGather& g) {
+    __shared__ uint32_t last_s, total_s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const bool last = atomicAdd(&g.cursor[2u + g.parity], 1u) == gridDim.x - 1;
+        if (last) { g.cursor[2u + g.parity] = 0; total_s = atomicAdd(&g.cursor[g.parity], 0u); }
+        last_s = last ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last_s) {
+        pkt_send_header(g, threadIdx.x, total_s);
+        // slice form: the padding of this rank's own slice (the peers zero their copies of it when the header arrives)
+        if (g.n_per) for (uint32_t k = total_s + threadIdx.x; k < g.n_per; k += blockDim.x) g.table[g.slot_base + k] = make_uint2(0u, 0u);
+    }
+}
+// one record to every peer at position pos of this rank's slice
+__device__ __forceinline__ void pkt_send(const PktGather& g, uint32_t pos, uint2 rec, uint32_t slot) {
+    const uint32_t y = pkt_tag(rec.y, g.epoch);
+    #pragma unroll 1
+    for (uint32_t p = 0; p < g.world; ++p)
+        if (p != g.rank) pkt_store(g.stage[p] + pos, rec.x, y, slot, g.epoch);
+}
+// Receive side, thread T of NT: poll the local staging slices until every peer's packets are in, scatter into the table.
+// A position is done when its packet is valid, or when the peer's header says nothing will come there.
+__device__ __forceinline__ void pkt_receive(const PktGather& g, uint32_t T, uint32_t NT, const Err& err) {
+    const uint32_t want_tag = pkt_tag(0u, g.epoch);
+    const long long t0 = clock64();
+    bool dead = false;
+    for (uint32_t r = 0; r < g.world && !dead; ++r) {
+        uint32_t n = 0xFFFFFFFFu;                                     // unknown until the header is in
+        if (r == g.rank) continue;                                    // own records went straight into the table
+        const uint4* sl = g.my_stage + (size_t)r * g.cap;
+        uint32_t spins = 0;
+        for (uint32_t k = T; !dead; ) {
+            if (n == 0xFFFFFFFFu) {
+                const uint4 h = pkt_load(g.my_hdr + r);
+                if (h.w == g.epoch && h.y == (h.x ^ g.epoch ^ 0xA5A5A5A5u)) {
+                    if (h.x == 0xFFFFFFFFu) { dead = true; break; }    // the peer aborted its batch
+                    n = min(h.x, g.cap);
+                }
+            }
+            if (n != 0xFFFFFFFFu && k >= n) break;
+            if (k < g.cap) {
+                const uint4 v = pkt_load(sl + k);
+                if (v.w == g.epoch && (v.y & ~PKT_CLEAN) == want_tag) {
+                    g.table[v.z] = make_uint2(v.x, v.y & PKT_CLEAN);
+                    k += NT; spins = 0;
+                    continue;
+                }
+            }
+            if ((++spins & 63u) == 0 && clock64() - t0 > g.spin_limit) dead = true;
+        }
+        if (g.n_per && !dead) for (uint32_t k = n + T; k < g.n_per; k += NT) g.table[(size_t)r * g.n_per + k] = make_uint2(0u, 0u);
+    }
+    if (dead) err.set(ERR_PEER_TIMEOUT);
+}
 
 // Direct host I/O of the single-launch kernel (k_fused): the CTAs themselves ingest the batch from the caller's
 // pinned (device-mapped) host buffers and write the OutRecs back there, instead of copy-engine transfers around the
@@ -801,6 +1011,7 @@ struct PackArgs {
     const uint4* claims;          // claims in input order                             (k_fused)
     const uint32_t* out_off;      // first out slot per claim or NULL                  (k_fused)
     uint32_t n_claim;             //                                                   (k_fused)
+    const uint32_t* n_dev;        // if set: the real number of claims (<= n_claim, which then only sizes the layout) (k_fused)
     const uint4* inv_src;         // inventory read from here ...
     uint4* inv_dst;               // ... and written back here (may alias inv_src)
     const uint32_t* node_off;     // [n_node+1]
@@ -809,7 +1020,7 @@ struct PackArgs {
     uint32_t n_out, n_node, have_off;
     Err err;
     SelCtx sel;                   // optional GPU attributes + selector table (spec §10)
-    PeerTail peer;                // world == 0: single GPU                            (k_fused)
+    PktGather peer;               // world == 0: single GPU                            (k_fused)
     unsigned long long* timeline; // optional instrumentation: 8 clock stamps per CTA  (k_fused), else NULL
     DirectIO dio;                 //                                                   (k_fused)
 };
@@ -1356,6 +1567,15 @@ k_fused(const PackArgs a) {
     const uint32_t list_addr = sbase + FU_LIST + (STAGE ? (uint32_t)NW * FU_MAXPIECE * 8u : 0u);
     const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(a.n_claim, NW, STAGE) + 15u) & ~15u) : 0u;
     const uint32_t sbar = sbase + FU_LIST;       // STAGE: one mbarrier per 4 KiB piece of the claim array
+    // sharded call: the claim list was compacted on the device by the kernel before this one; a.n_claim is its capacity
+    const uint32_t n_claim = a.n_dev ? min(a.n_claim, __ldcg(a.n_dev)) : a.n_claim;
+    if (a.n_dev && __ldcg(a.n_dev) > a.n_claim) {            // laid out for fewer claims: touch nothing, tell everybody
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) a.err.set(ERR_SHARD_PLAN);
+            if (a.peer.world) pkt_send_header(a.peer, threadIdx.x, 0xFFFFFFFFu);
+        }
+        return;
+    }
 
     // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
     uint32_t g0 = 0, g1 = 0;
@@ -1386,11 +1606,11 @@ k_fused(const PackArgs a) {
         if (CL > 1) { cluster_arrive(); cluster_wait(); }      // barriers initialised in every CTA of the cluster before any multicast
         // every warp arms (and, for the pieces this CTA is responsible for, issues) its share of the pieces:
         // TMA issues from one warp serialise (~100 cycles each), so they are spread over the 8 warps' lane 0
-        const uint32_t npt = (a.n_claim + FU_PIECE - 1) / FU_PIECE;
+        const uint32_t npt = (n_claim + FU_PIECE - 1) / FU_PIECE;
         const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
         if (lane == 0)
             for (uint32_t g = wid; g < npt; g += NW) {
-                const uint32_t c0 = g * FU_PIECE, bytes = min(FU_PIECE, a.n_claim - c0) * 16u;
+                const uint32_t c0 = g * FU_PIECE, bytes = min(FU_PIECE, n_claim - c0) * 16u;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar + g * 8), "r"(bytes) : "memory");
                 if (g % CL == crank) {
                     if (CL > 1) tma_load_multicast(stage_addr + (c0 << 4), a.claims + c0, bytes, sbar + g * 8, (uint16_t)((1u << CL) - 1u));
@@ -1419,15 +1639,15 @@ k_fused(const PackArgs a) {
     }
 
     // ---- filter: which claims select this node (all warps) ------------------------------------------
-    const uint32_t chunk = fused_chunk(a.n_claim, NW, STAGE);          // per-warp part
-    const uint32_t lo = wid * chunk, hi = min(a.n_claim, lo + chunk);
+    const uint32_t chunk = fused_chunk(n_claim, NW, STAGE);            // per-warp part
+    const uint32_t lo = wid * chunk, hi = min(n_claim, lo + chunk);
     const uint32_t ltmask = lanemask_lt();
     const uint32_t my_list = list_addr + (lo << 2);
     const uint32_t want = has_node ? node : 0xFFFFFFFEu;
     uint32_t cntw = 0;
     if (node == a.n_node) {
         // claims that name no node of the inventory: INVALID (spec §3); no state is touched
-        for (uint32_t i = threadIdx.x; i < a.n_claim; i += NW * 32) {
+        for (uint32_t i = threadIdx.x; i < n_claim; i += NW * 32) {
             const uint4 c = __ldcg(&a.claims[i]);              // L2: direct mode wrote the copy inside this kernel
             if (c.y < a.n_node) continue;
             const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
@@ -1436,7 +1656,6 @@ k_fused(const PackArgs a) {
             if (dst < a.n_out) {
                 const uint2 r_ = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
                 a.out[dst] = r_;
-                for (uint32_t p = 0; p < a.peer.world; ++p) if (p != a.peer.rank) a.peer.peer_out[p][dst] = r_;
             } else a.err.set(ERR_OUT_RANGE);
         }
     }
@@ -1550,47 +1769,66 @@ k_fused(const PackArgs a) {
     }
     if (a.peer.world == 0) return;
 
-    // ---- multi-GPU tail: all-gather by peer stores, fused here (no extra launch) -------------------------
-    // 1. every CTA pushes the OutRecs of ITS node's claims into the same slots of every peer's table
+    // ---- multi-GPU tail: the all-gather, fused here (no extra launch, no fence, no flag) -----------------------
+    // 1. every CTA sends the OutRecs of ITS node's claims as packets into a contiguous range of this rank's slice at
+    //    every peer; 2. every CTA then polls its share of the peers' slices in local memory and fills the table.
     __syncthreads();                                   // warp 0's OutRecs are visible to the whole CTA
-    const PeerTail& pt = a.peer;
+    const PktGather& pg = a.peer;
+    __shared__ uint32_t pk_total_s, pk_base_s, pk_next_s;
+    if (threadIdx.x == 0) { pk_total_s = 0; pk_next_s = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 32) pg.cursor[pg.parity ^ 1u] = 0;       // the next call's cursor
+    __syncthreads();
+    // the claims this CTA answers for: its node's list, or (CTA n_node) the claims that name no node
+    const bool stray_cta = node == a.n_node;
+    auto slots_of = [&](const uint4 c) -> uint32_t {
+        const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
+        return (kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
+    };
+    auto claim_at = [&](uint32_t i) -> uint4 { return STAGE ? lds128(stage_addr + (i << 4)) : __ldcg(&a.claims[i]); };
+    uint32_t mine = 0;
     if (has_node) {
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
-            const uint4 c = STAGE ? lds128(stage_addr + (i << 4)) : __ldg(&a.claims[i]);
+            const uint4 c = claim_at(i);
+            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(c);
+            if (!(dst > a.n_out || sl > a.n_out - dst)) mine += sl;
+        }
+    } else if (stray_cta) {
+        for (uint32_t i = threadIdx.x; i < n_claim; i += NW * 32) {
+            if (__ldcg(&a.claims[i]).y < a.n_node) continue;
             const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
-            const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
-            const uint32_t slots = (kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
-            if (dst > a.n_out || slots > a.n_out - dst) continue;
-            for (uint32_t s_ = 0; s_ < slots; ++s_) {
-                const uint2 r_ = a.out[dst + s_];
-                for (uint32_t p = 0; p < pt.world; ++p) if (p != pt.rank) pt.peer_out[p][dst + s_] = r_;
+            if (dst < a.n_out) mine += 1;
+        }
+    }
+    mine = __reduce_add_sync(FULLMASK, mine);
+    if (lane == 0 && mine) atomicAdd(&pk_total_s, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && pk_total_s) pk_base_s = atomicAdd(&pg.cursor[pg.parity], pk_total_s);
+    __syncthreads();
+    if (pk_total_s) {
+        const uint32_t base = pk_base_s;
+        auto send = [&](uint32_t dst, uint32_t sl) {
+            const uint32_t at = base + atomicAdd(&pk_next_s, sl);
+            for (uint32_t s_ = 0; s_ < sl; ++s_)
+                if (at + s_ < pg.cap) pkt_send(pg, at + s_, __ldcg(a.out + dst + s_), pg.slot_base + dst + s_);
+        };
+        if (has_node) {
+            for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
+                const uint32_t i = get.index_of(m);
+                const uint4 c = claim_at(i);
+                const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(c);
+                if (!(dst > a.n_out || sl > a.n_out - dst)) send(dst, sl);
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < n_claim; i += NW * 32) {
+                if (__ldcg(&a.claims[i]).y < a.n_node) continue;
+                const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
+                if (dst < a.n_out) send(dst, 1u);
             }
         }
     }
-    __syncthreads();
-    // 2. the last CTA to get here publishes this rank's epoch to every peer and waits for theirs.
-    //    One system fence per CTA: bar.sync orders the CTA's stores before thread 0, fences are cumulative.
-    __shared__ uint32_t last_s;
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        last_s = atomicAdd(pt.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!last_s) return;
-    if (threadIdx.x == 0) { *pt.ticket = 0; __threadfence_system(); }
-    __syncthreads();
-    if (threadIdx.x < pt.world) {
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[threadIdx.x] + pt.rank), "r"(pt.epoch) : "memory");
-        const uint32_t* f = pt.flags[pt.rank] + threadIdx.x;
-        const long long t0 = clock64();
-        uint32_t v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if ((int32_t)(v - pt.epoch) >= 0) break;
-            if (clock64() - t0 > 400000000ll) { a.err.set(ERR_PEER_TIMEOUT); break; }   // ~0.2 s: fail, do not hang
-        } while (true);
-    }
+    pkt_finish_send(pg);                               // the last CTA to get here tells the peers how many packets went out
+    pkt_receive(pg, blockIdx.x * (NW * 32) + threadIdx.x, gridDim.x * (NW * 32), a.err);
 }
 
 // ====================================================================================================
@@ -1921,67 +2159,41 @@ k_dealloc(const uint4* __restrict__ claims, uint32_t n_claim, const uint32_t* __
 
 
 // ====================================================================================================
-// peer all-gather: the path's one collective as NVLink P2P stores instead of a library call
+// the all-gather as its own kernel (sort path: the pack kernel has no tail), same packets as k_fused's tail
 // ====================================================================================================
-// Every rank owns a buffer  [2 parities][world][n_per] OutRec  + flag words, IPC-mapped into every peer.
-//   k_peer_push   this rank's slice -> the same slot of every peer's buffer (16-byte coalesced stores over
-//                 NVLink), system fence, then the last CTA publishes the epoch in every peer's flag word
-//   k_peer_wait   spins (bounded) until every rank's flag shows the epoch, then copies the complete table
-//                 to the caller's buffer
-// Parity alternates per call, so a rank can push epoch e+1 while a slow peer still reads epoch e.
-struct PeerArgs {
-    uint4* buf[PEER_MAX];         // peer buffers (buf[rank] is local)
-    uint32_t* flags[PEER_MAX];    // peer flag arrays, one word per source rank
-    uint32_t* ticket;             // local
-    uint32_t world, rank, n_per16; // n_per16 = uint4s per rank slice
-    uint32_t epoch, parity;
-    Err err;
-};
-
+// claims[0..n) are THIS rank's claims (input order or sorted, any order), out_off their first local slot (NULL: slot i);
+// their OutRecs already sit in the local table at slot_base + slot.  Thread per claim: send; then everybody receives.
 __global__ void __launch_bounds__(256)
-k_peer_push(const PeerArgs a) {
-    const size_t slot = ((size_t)a.parity * a.world + a.rank) * a.n_per16;
-    const uint4* src = a.buf[a.rank] + slot;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t p = 0; p < a.world; ++p) {
-        if (p == a.rank) continue;
-        uint4* dst = a.buf[p] + slot;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_per16; i += stride) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t t = atomicAdd(a.ticket, 1u);
-        if (t == gridDim.x - 1) {                       // every CTA's stores are fenced: publish
-            *a.ticket = 0;
-            __threadfence_system();
-            for (uint32_t p = 0; p < a.world; ++p)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[p] + a.rank), "r"(a.epoch) : "memory");
+k_pkt_gather(const PktGather g, const uint4* __restrict__ claims, uint32_t n_claim, const uint32_t* __restrict__ n_dev,
+             const uint32_t* __restrict__ out_off, uint32_t n_out, uint32_t have_off, uint32_t n_node, Err err) {
+    const uint32_t T = blockIdx.x * blockDim.x + threadIdx.x, NT = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    if (n_dev) n_claim = min(n_claim, __ldcg(n_dev));
+    if (blockIdx.x == 0 && threadIdx.x == 32) g.cursor[g.parity ^ 1u] = 0;
+    const uint2* local = g.table + g.slot_base;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n_claim; i0 += NT) {
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t sl = 0, dst = 0;
+        if (i < n_claim) {
+            const uint4 c = __ldcg(&claims[i]);
+            const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
+            dst = out_off ? __ldcg(&out_off[i]) : i;
+            sl = (kind == DRA_KIND_GPU && c.y < n_node && !claim_invalid(kind, 0, count, have_off != 0)) ? count : 1u;
+            if (dst > n_out || sl > n_out - dst) sl = 0;
         }
+        // one reservation per warp: contiguous packets, 128-byte lines on the wire
+        uint32_t incl = sl;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, incl, d); if (lane >= (uint32_t)d) incl += y; }
+        const uint32_t tot = __shfl_sync(FULLMASK, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && tot) base = atomicAdd(&g.cursor[g.parity], tot);
+        base = __shfl_sync(FULLMASK, base, 0) + incl - sl;
+        for (uint32_t s_ = 0; s_ < sl; ++s_)
+            if (base + s_ < g.cap) pkt_send(g, base + s_, __ldcg(local + dst + s_), g.slot_base + dst + s_);
     }
+    pkt_finish_send(g);
+    pkt_receive(g, T, NT, err);
 }
-
-__global__ void __launch_bounds__(256)
-k_peer_wait(const PeerArgs a, uint4* __restrict__ user_out) {
-    if (threadIdx.x < a.world) {
-        const uint32_t* f = a.flags[a.rank] + threadIdx.x;
-        const long long t0 = clock64();
-        uint32_t v;
-        bool ok = true;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if ((int32_t)(v - a.epoch) >= 0) break;
-            if (clock64() - t0 > 400000000ll) { ok = false; break; }     // ~0.2 s: a peer is gone; fail, do not hang
-        } while (true);
-        if (!ok) a.err.set(ERR_PEER_TIMEOUT);
-    }
-    __syncthreads();
-    if (!user_out) return;                         // the table stays in the IPC buffer (dra_gather_table)
-    const uint4* src = a.buf[a.rank] + (size_t)a.parity * a.world * a.n_per16;
-    const uint32_t n = a.world * a.n_per16, stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) user_out[i] = src[i];
-}
-
 
 // ====================================================================================================
 // adjacent integer searches of the reference, batched (API completeness)

@@ -2,7 +2,7 @@
 """Multi-GPU parity check (run under torchrun on N >= 2 GPUs of one box; not collected by pytest — the round-end
 GPU suite runs on one GPU).  Every rank allocates its shard and all-gathers; every rank then compares the WHOLE
 gathered table, merged back to global input order, with the CPU oracle on the global batch.  Paths covered:
-fused kernel + peer-store tail, sort path + peer push/wait kernels, and ncclAllGather; claims with counts > 1
+fused kernel + packet-gather tail, sort path + gather kernel, ncclAllGather, and the sharded GLOBAL batch; claims with counts > 1
 (out_off), co-location groups, malformed claims.
 
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
@@ -56,6 +56,33 @@ for name, w, ctx_flags, use_peer in [
         fails += not ok
         if rank == 0:
             print(f"{name} rep {rep}: {'OK' if ok else 'MISMATCH'} ({w.n_claim} claims, {world} ranks)")
+    ctx.close()
+# ---- the sharded GLOBAL batch: the same claim array on every rank, device-side range filter, global slots ----
+for name, w, ctx_flags in [("global batch, fused, mixed", pkg.synth.mixed(9000, 97, 31), 0),
+                           ("global batch, sort path", pkg.synth.mixed(30000, 200, 32), pkg.api.CFG_NO_FUSED),
+                           ("global batch, cfg3/4", pkg.synth.cfg2(25000, 250), 0)]:
+    ranges = pkg.shard.plan(w.claims["node"], w.n_node, world)
+    ctx = pkg.api.Context(device=local, stream=stream.cuda_stream, flags=ctx_flags)
+    ctx.set_table(w.table); ctx.set_inventory(w.gpus, w.node_off)
+    uid = [pkg.api.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    ctx.set_shard(ranges[rank][0], ranges[rank][1], take_stray=(rank == 0))
+    hs = [None] * world
+    dist.all_gather_object(hs, ctx.shard_export(w.n_out))
+    ctx.peer_import(hs)
+    d_claims = torch.from_numpy(w.claims.view(np.uint8).copy()).to(dev)
+    d_off = None if w.out_off is None else torch.from_numpy(w.out_off.view(np.uint8).copy()).to(dev)
+    ref, ref_inv = O.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+    for rep in range(3):
+        ctx.allocate_global_device(d_claims.data_ptr(), w.n_claim, None if d_off is None else d_off.data_ptr(), w.n_out, pkg.api.F_FRESH_INVENTORY)
+        table = ctx.gather_read(np.zeros(w.n_out, dtype=R.OUT_DTYPE))
+        g0, g1 = int(w.node_off[ranges[rank][0]]), int(w.node_off[ranges[rank][1]])
+        ok = table.tobytes() == ref.tobytes() and ctx.get_inventory()[g0:g1].tobytes() == ref_inv[g0:g1].tobytes()
+        fails += not ok
+        if rank == 0:
+            print(f"{name} rep {rep}: {'OK' if ok else 'MISMATCH'} ({w.n_claim} claims, {world} ranks)")
+    dist.barrier()
     ctx.close()
 t = torch.tensor([fails], device=dev); dist.all_reduce(t)
 if rank == 0:
