@@ -107,7 +107,9 @@ struct dra_ctx {
     bool ev_ok = false;
     float timings[5] = {0, 0, 0, 0, 0};
     uint32_t ev_mask = 0;
-    int hist8_smem_set = 0, hist_smem_set = 0, small_smem_set = 0, fused_smem_set = 0, fused_smem_set_stage = 0, fused_smem_set_cl = 0;
+    // dynamic shared-memory limits are raised ONCE per device to the opt-in maximum (raise_smem_limits): the attribute is
+    // per function, not per context — a lazily "grown" per-context value would LOWER it under another context's feet
+    int hist8_smem_set = 1 << 30, hist_smem_set = 1 << 30, small_smem_set = 1 << 30, fused_smem_set = 1 << 30, fused_smem_set_stage = 1 << 30, fused_smem_set_cl = 1 << 30;
     uint64_t fused_max_work = 3000000ull;   // n_node * n_claim up to which the single-launch kernel is used
     // direct host I/O of the single-launch kernel (DirectIO in dra_device.cuh)
     DirectIO dio_pending{};                 // set by dra_allocate_batch for the next launch_allocate, then cleared
@@ -312,7 +314,8 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
             Prefetch pf;
             pf.p[0] = inv_src;
             pf.bytes[0] = std::min<uint32_t>(ctx->n_gpu * 16u, 1u << 20) & ~15u;
-            pf.p[1] = d_node_off; pf.bytes[1] = std::min<uint32_t>((n_node + 1) * 4u, 1u << 20) & ~15u;
+            pf.p[1] = (const void*)((uintptr_t)d_node_off & ~(uintptr_t)15);      // (a shard's view starts mid-array: bulk prefetch wants 16-byte alignment)
+            pf.bytes[1] = std::min<uint32_t>((n_node + 1) * 4u, 1u << 20) & ~15u;
             pf.p[2] = ctx->d_tbl; pf.bytes[2] = 1024;
             k_bucket_small<<<1, 1024, small_smem, ctx->stream>>>(d_claims, n_claim, n_node, d_out_off, ctx->d_claim_off,
                                                                  ctx->d_sorted, d_out, n_out, err, pf, n_dev);
@@ -460,8 +463,8 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
             lc.attrs = at; lc.numAttrs = 1;
             CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, true, 1>, a));
         }
-        else if (stage) k_fused<FUSED_NW, true, 1><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
-        else k_fused<FUSED_NW, false, 1><<<n_node + 1, FUSED_NW * 32, fused_smem, ctx->stream>>>(a);
+        else if (stage) CU(launch_k(k_fused<FUSED_NW, true, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), fused_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
+        else CU(launch_k(k_fused<FUSED_NW, false, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), fused_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
         ctx->launches += 1;
         prof.mark();
         cudaError_t e = cudaGetLastError();
@@ -512,6 +515,27 @@ int check_err(dra_ctx* ctx) {
 
 }  // namespace
 
+namespace {
+template <class K>
+int raise_one(dra_ctx* ctx, K k, int optin) {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, k));
+    const int dyn = optin - (int)fa.sharedSizeBytes;          // the opt-in limit covers static + dynamic
+    if (dyn > 48 * 1024) CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    return DRA_OK;
+}
+int raise_smem_limits(dra_ctx* ctx, int optin) {
+    int rc;
+    if ((rc = raise_one(ctx, k_fused<FUSED_NW, true, 1>, optin))) return rc;
+    if ((rc = raise_one(ctx, k_fused<FUSED_NW, false, 1>, optin))) return rc;
+    if ((rc = raise_one(ctx, k_fused<FUSED_NW, true, 8>, optin))) return rc;
+    if ((rc = raise_one(ctx, k_bucket_small, optin))) return rc;
+    if ((rc = raise_one(ctx, k_bucket_hist8, optin))) return rc;
+    if ((rc = raise_one(ctx, k_bucket_hist, optin))) return rc;
+    return DRA_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int dra_abi_version(void) { return (int)DRA_ABI_VERSION; }
@@ -538,6 +562,7 @@ int dra_ctx_create(const dra_cfg* cfg, dra_ctx** out) {
     c->coop_ok = prop.cooperativeLaunch && prop.unifiedAddressing && prop.canUseHostPointerForRegisteredMem;
     ctx = c;
     auto bail = [&](int rc) { g_create_err = c->err; dra_ctx_destroy(c); return rc; };
+    { int rc = raise_smem_limits(c, (int)prop.sharedMemPerBlockOptin); if (rc) return bail(rc); }
     if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
     else {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(c, DRA_E_CUDA, "cudaStreamCreate"));
@@ -892,9 +917,15 @@ int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
         const uint32_t W = ctx->max_width <= 8 ? 8u : (ctx->max_width <= 16 ? 16u : 32u);
         const uint32_t per_cta = 8 * (32 / W);
         const uint32_t grid = std::max(1u, std::min((n_pair + per_cta - 1) / per_cta, (uint32_t)ctx->n_sm * 8u));
-        if (W == 8) k_unsuitable<8, 8><<<grid, 256, 0, ctx->stream>>>(a);
-        else if (W == 16) k_unsuitable<8, 16><<<grid, 256, 0, ctx->stream>>>(a);
-        else k_unsuitable<8, 32><<<grid, 256, 0, ctx->stream>>>(a);
+        if (a.exhaustive) {
+            if (W == 8) k_unsuitable<8, 8, true><<<grid, 256, 0, ctx->stream>>>(a);
+            else if (W == 16) k_unsuitable<8, 16, true><<<grid, 256, 0, ctx->stream>>>(a);
+            else k_unsuitable<8, 32, true><<<grid, 256, 0, ctx->stream>>>(a);
+        } else {
+            if (W == 8) k_unsuitable<8, 8, false><<<grid, 256, 0, ctx->stream>>>(a);
+            else if (W == 16) k_unsuitable<8, 16, false><<<grid, 256, 0, ctx->stream>>>(a);
+            else k_unsuitable<8, 32, false><<<grid, 256, 0, ctx->stream>>>(a);
+        }
         prof.mark();
         ctx->launches += 1;
         if ((rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, words * 4))) return rc;
@@ -1217,11 +1248,31 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     if (gather && n_out > ctx->peer_tab_len) return fail(ctx, DRA_E_INVAL, "n_out %u exceeds the exported table (%u)", n_out, ctx->peer_tab_len);
     CU(cudaSetDevice(ctx->device));
     const uint32_t n_local_node = ctx->shard_hi - ctx->shard_lo;
-    // plan from the previous call's count (first call: an even split), with slack; the buffers always hold n_claim
-    uint32_t expect = ctx->h_sc_counts && ctx->h_sc_counts[2] == 1u ? ctx->h_sc_counts[0]
-                                                                    : (uint32_t)((uint64_t)n_claim / (uint32_t)std::max(1, ctx->world));
-    uint32_t cap = std::min<uint64_t>(n_claim, (uint64_t)expect + expect / 10 + 128);
+    // Plan.  The single-launch kernel lays its shared memory out for a CAPACITY of claims; the real number is only known
+    // on the device (the compaction's count).  First call of a shape: capacity = the whole batch (always safe).  Later
+    // calls: the last completed call's count plus slack — as much slack as still lets the claim array be STAGED in shared
+    // memory (the fast form).  If more claims than the capacity fall into the shard the kernel touches nothing, tells its
+    // peers, and the call fails with DRA_E_STATE ("call again": the next plan uses the new count).
+    uint32_t cap = n_claim;
     FusedPlan plan = fused_plan(ctx, cap, flags, n_local_node);
+    if (ctx->h_sc_counts && ctx->h_sc_counts[3] != 0u) {
+        const uint32_t expect = ctx->h_sc_counts[0];
+        const uint32_t hi = (uint32_t)std::min<uint64_t>(n_claim, (uint64_t)expect + expect / 4 + 256);
+        const uint32_t lo = (uint32_t)std::min<uint64_t>(n_claim, (uint64_t)expect + expect / 32 + 64);
+        FusedPlan ph = fused_plan(ctx, hi, flags, n_local_node);
+        cap = hi; plan = ph;
+        if (ph.fused && !ph.stage) {                            // shrink the slack until the array fits shared memory
+            for (uint32_t c = hi; c >= lo; c -= std::max(1u, (hi - lo) / 16u)) {
+                const FusedPlan pc = fused_plan(ctx, c, flags, n_local_node);
+                if (pc.fused && pc.stage) { cap = c; plan = pc; break; }
+                if (c == lo || c - lo < std::max(1u, (hi - lo) / 16u)) {
+                    const FusedPlan pl = fused_plan(ctx, lo, flags, n_local_node);
+                    if (pl.fused && pl.stage) { cap = lo; plan = pl; }
+                    break;
+                }
+            }
+        }
+    }
     if (!plan.fused) cap = n_claim;                           // sort path: no layout depends on the count
     int rc = ensure_batch(ctx, std::max(cap, 1u), n_out, false);
     if (rc) return rc;
@@ -1272,7 +1323,6 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     sa.counts = ctx->d_sc_counts; sa.h_counts = ctx->h_sc_counts_dev; sa.err = err_of(ctx);
     k_shard_compact<<<n_tiles, 256, 0, ctx->stream>>>(sa);
     ctx->launches += 1;
-    ctx->h_sc_counts[2] = 1u;                                 // (host-side note: counts of a call exist from now on)
     // 2. the usual chain on the shard's view of the inventory, results at the claims' GLOBAL slots
     AllocView view; view.node_lo = ctx->shard_lo; view.n_node = n_local_node; view.n_dev = ctx->d_sc_counts; view.have_off = d_out_off != nullptr;
     bool tail_done = false;

@@ -800,6 +800,7 @@ __global__ void __launch_bounds__(256)
 k_shard_compact(const ShardArgs a) {
     __shared__ uint32_t tile_s, rowc[64], rows[64], pre_c, pre_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ltm = lanemask_lt();
+    pdl_trigger();                                           // the allocation kernel's prologue may overlap this kernel
     if (tid == 0) {
         const uint32_t t = atomicAdd(a.ticket, 1u);
         if (t == a.n_tiles - 1) *a.ticket = 0;                    // the last ticket of this launch: ready for the next
@@ -865,7 +866,7 @@ k_shard_compact(const ShardArgs a) {
             pre_c = ec; pre_s = es;
             if (tile == a.n_tiles - 1) {
                 a.counts[0] = ec + tc; a.counts[1] = es + ts;
-                a.h_counts[0] = ec + tc; a.h_counts[1] = es + ts;
+                a.h_counts[0] = ec + tc; a.h_counts[1] = es + ts; a.h_counts[3] = a.epoch;
             }
         }
     }
@@ -1567,16 +1568,6 @@ k_fused(const PackArgs a) {
     const uint32_t list_addr = sbase + FU_LIST + (STAGE ? (uint32_t)NW * FU_MAXPIECE * 8u : 0u);
     const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(a.n_claim, NW, STAGE) + 15u) & ~15u) : 0u;
     const uint32_t sbar = sbase + FU_LIST;       // STAGE: one mbarrier per 4 KiB piece of the claim array
-    // sharded call: the claim list was compacted on the device by the kernel before this one; a.n_claim is its capacity
-    const uint32_t n_claim = a.n_dev ? min(a.n_claim, __ldcg(a.n_dev)) : a.n_claim;
-    if (a.n_dev && __ldcg(a.n_dev) > a.n_claim) {            // laid out for fewer claims: touch nothing, tell everybody
-        if (blockIdx.x == 0) {
-            if (threadIdx.x == 0) a.err.set(ERR_SHARD_PLAN);
-            if (a.peer.world) pkt_send_header(a.peer, threadIdx.x, 0xFFFFFFFFu);
-        }
-        return;
-    }
-
     // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
     uint32_t g0 = 0, g1 = 0;
     if (has_node) { g0 = __ldg(&a.node_off[node]); g1 = __ldg(&a.node_off[node + 1]); }
@@ -1588,6 +1579,17 @@ k_fused(const PackArgs a) {
     if (threadIdx.x == 0) tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
     const uint32_t ng = g1 - g0;
     if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
+    // sharded call: the claim list was compacted on the device by the kernel before this one; a.n_claim is its capacity
+    if (a.n_dev) pdl_wait();                                 // (launched as a programmatic dependent of the compaction)
+    const uint32_t n_claim = a.n_dev ? min(a.n_claim, __ldcg(a.n_dev)) : a.n_claim;
+    if (a.n_dev && __ldcg(a.n_dev) > a.n_claim) {            // laid out for fewer claims: touch nothing, tell everybody
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) a.err.set(ERR_SHARD_PLAN);
+            if (a.peer.world) { pkt_send_header(a.peer, threadIdx.x, 0xFFFFFFFFu); if (threadIdx.x == 32) a.peer.cursor[a.peer.parity ^ 1u] = 0; }
+        }
+        return;
+    }
+
     if (STAGE && CL == 1 && a.dio.h_claims) {
         // direct ingest: one 16-byte load from the caller's pinned buffer per thread (a single PCIe round trip for
         // the whole grid), stored to the device copy that everybody's bulk copies below read from L2.
@@ -2082,7 +2084,7 @@ struct GlobalGet {
 // W lanes per (pod, candidate) pair: 32/W pairs share a warp (W = 8 for the usual <= 8 GPUs per node), each
 // group running its own claim loop with group-wide ballots.  dense = every pod against every node
 // (pair = pod * n_node + node): no candidate arrays at all.
-template <int WPC, int W>
+template <int WPC, int W, bool EXH>                    // EXH: spec §12 (own instantiation: the default kernel stays as lean as it was)
 __global__ void __launch_bounds__(WPC * 32, 2)
 k_unsuitable(const UnsArgs a) {
     __shared__ uint32_t tbl_s[DRA_MAX_MODELS * DRA_MAX_PROFILES];
@@ -2107,7 +2109,7 @@ k_unsuitable(const UnsArgs a) {
         uint4 rec = make_uint4(0, 0, 0, 0);
         if (gl < ng) rec = __ldg(&a.inv[g0 + gl]);
         Lane L; L.load(rec, gl < ng);
-        if (a.exhaustive) {                                               // spec §12
+        if (EXH) {                                                        // spec §12
             if (cnt > DRA_MAX_POD || ng > W) continue;
             const PodGet pget{a.claims + c0, nullptr, 0};
             Lane Lt = L;                                                    // by copy: a reference would pin L in local memory

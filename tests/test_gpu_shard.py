@@ -73,11 +73,29 @@ def test_sharded_global_batch_world1_and_empty_shards(pkg, oracle):
         for c in ctxs:
             c.peer_import_local(ctxs)
         d = _dev(w.claims)
-        for _ in range(2):
+        for _ in range(3):
             for c in ctxs:
                 c.allocate_global_device(d.data_ptr(), w.n_claim, None, w.n_out, pkg.api.F_FRESH_INVENTORY)
             for c in ctxs:
                 assert c.gather_read(np.zeros(w.n_out, dtype=R.OUT_DTYPE)).tobytes() == ref.tobytes()
+        # the distribution shifts under a plan made for the old one: every claim now lands in rank 1's range.  The call
+        # fails WITHOUT touching anything ("call again"), the peers are told at once (no time-out), the retry succeeds.
+        w2 = pkg.synth.cfg2(3000, 12); w2.claims["node"] = 5 + w2.claims["node"] % 7
+        ref2, _ = oracle.allocate(w2.gpus, w2.node_off, w2.table, w2.claims)
+        d2 = _dev(w2.claims)
+        for c in ctxs:
+            c.allocate_global_device(d2.data_ptr(), w2.n_claim, None, w2.n_out, pkg.api.F_FRESH_INVENTORY)
+        errs = []
+        for c in ctxs:
+            try:
+                c.gather_read(np.zeros(w2.n_out, dtype=R.OUT_DTYPE))
+            except pkg.api.DraError as e:
+                errs.append(e.code)
+        assert pkg.api.E_STATE in errs, errs
+        for c in ctxs:
+            c.allocate_global_device(d2.data_ptr(), w2.n_claim, None, w2.n_out, pkg.api.F_FRESH_INVENTORY)
+        for c in ctxs:
+            assert c.gather_read(np.zeros(w2.n_out, dtype=R.OUT_DTYPE)).tobytes() == ref2.tobytes()
     finally:
         for c in ctxs:
             c.close()
