@@ -1646,23 +1646,11 @@ k_fused(const PackArgs a) {
     const uint32_t ltmask = lanemask_lt();
     const uint32_t my_list = list_addr + (lo << 2);
     const uint32_t want = has_node ? node : 0xFFFFFFFEu;
+    const bool stray_cta = node == a.n_node;
     uint32_t cntw = 0;
-    if (node == a.n_node) {
-        // claims that name no node of the inventory: INVALID (spec §3); no state is touched
-        for (uint32_t i = threadIdx.x; i < n_claim; i += NW * 32) {
-            const uint4 c = __ldcg(&a.claims[i]);              // L2: direct mode wrote the copy inside this kernel
-            if (c.y < a.n_node) continue;
-            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
-            const uint32_t kind = c.x & 0xFFu;
-            const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
-            if (dst < a.n_out) {
-                const uint2 r_ = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
-                a.out[dst] = r_;
-            } else a.err.set(ERR_OUT_RANGE);
-        }
-    }
     auto scan = [&](const uint32_t i, const uint32_t keyv) {          // one claim per lane; warp-uniform control flow
-        const bool m = has_node && keyv == want;
+        // CTA n_node collects the claims that name no node of the inventory (they become INVALID, spec §3)
+        const bool m = has_node ? keyv == want : (stray_cta && i < hi && keyv >= a.n_node);
         const uint32_t b = __ballot_sync(FULLMASK, m);
         if (b) {
             if (m) sts32(my_list + ((cntw + (uint32_t)__popc(b & ltmask)) << 2), i);
@@ -1716,6 +1704,17 @@ k_fused(const PackArgs a) {
     #pragma unroll
     for (int i = 0; i < NW; ++i) { get.pre[i] = cnt; cnt += lds32(sbase + FU_CNT + (i << 2)); }
 
+    if (stray_cta) {                               // claims naming no node: INVALID (spec §3); no state is touched
+        for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
+            const uint32_t i = get.index_of(m);
+            const uint4 c = STAGE ? lds128(stage_addr + (i << 4)) : __ldcg(&a.claims[i]);
+            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
+            const uint32_t kind = c.x & 0xFFu;
+            const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
+            if (dst < a.n_out) a.out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+            else a.err.set(ERR_OUT_RANGE);
+        }
+    }
     // ---- pack: warp 0 ----------------------------------------------------------------------------------
     if (wid == 0 && has_node) {
         if (cnt == 0) {
@@ -1780,26 +1779,18 @@ k_fused(const PackArgs a) {
     if (threadIdx.x == 0) { pk_total_s = 0; pk_next_s = 0; }
     if (blockIdx.x == 0 && threadIdx.x == 32) pg.cursor[pg.parity ^ 1u] = 0;       // the next call's cursor
     __syncthreads();
-    // the claims this CTA answers for: its node's list, or (CTA n_node) the claims that name no node
-    const bool stray_cta = node == a.n_node;
+    // the claims this CTA answers for: its node's list, or (CTA n_node) the claims that name no node (one slot each)
     auto slots_of = [&](const uint4 c) -> uint32_t {
         const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
-        return (kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
+        return (!stray_cta && kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
     };
     auto claim_at = [&](uint32_t i) -> uint4 { return STAGE ? lds128(stage_addr + (i << 4)) : __ldcg(&a.claims[i]); };
     uint32_t mine = 0;
-    if (has_node) {
+    if (has_node || stray_cta) {
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
-            const uint4 c = claim_at(i);
-            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(c);
+            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(claim_at(i));
             if (!(dst > a.n_out || sl > a.n_out - dst)) mine += sl;
-        }
-    } else if (stray_cta) {
-        for (uint32_t i = threadIdx.x; i < n_claim; i += NW * 32) {
-            if (__ldcg(&a.claims[i]).y < a.n_node) continue;
-            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
-            if (dst < a.n_out) mine += 1;
         }
     }
     mine = __reduce_add_sync(FULLMASK, mine);
@@ -1809,24 +1800,13 @@ k_fused(const PackArgs a) {
     __syncthreads();
     if (pk_total_s) {
         const uint32_t base = pk_base_s;
-        auto send = [&](uint32_t dst, uint32_t sl) {
+        for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
+            const uint32_t i = get.index_of(m);
+            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(claim_at(i));
+            if (dst > a.n_out || sl > a.n_out - dst) continue;
             const uint32_t at = base + atomicAdd(&pk_next_s, sl);
             for (uint32_t s_ = 0; s_ < sl; ++s_)
                 if (at + s_ < pg.cap) pkt_send(pg, at + s_, __ldcg(a.out + dst + s_), pg.slot_base + dst + s_);
-        };
-        if (has_node) {
-            for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
-                const uint32_t i = get.index_of(m);
-                const uint4 c = claim_at(i);
-                const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(c);
-                if (!(dst > a.n_out || sl > a.n_out - dst)) send(dst, sl);
-            }
-        } else {
-            for (uint32_t i = threadIdx.x; i < n_claim; i += NW * 32) {
-                if (__ldcg(&a.claims[i]).y < a.n_node) continue;
-                const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
-                if (dst < a.n_out) send(dst, 1u);
-            }
         }
     }
     pkt_finish_send(pg);                               // the last CTA to get here tells the peers how many packets went out
