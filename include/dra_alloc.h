@@ -169,6 +169,12 @@ typedef struct dra_cfg {
                                     results to the pinned host buffers itself (direct host I/O, one cooperative launch);
                                     always use copy-engine transfers around the kernels */
 
+#define DRA_CFG_RESIDENT   0x8u  /* dra_allocate_batch: keep the single-launch kernel RESIDENT and hand it batches by doorbell (a command
+                                    line + sequence number in mapped host memory, completion word back) — no kernel launch, no stream
+                                    call per batch.  Applies to batches that fit the staged single-launch form on an inventory of at most
+                                    (SMs - 1) nodes with page-locked buffers; everything else stops the resident kernel first and takes
+                                    the usual path.  The kernel leaves by itself after DRA_SERVE_IDLE_MS (20) ms without a batch. */
+
 /* error codes (negative) */
 #define DRA_OK        0
 #define DRA_E_INVAL  (-1)
@@ -322,6 +328,13 @@ int  dra_mps_limits_batch(dra_ctx* ctx, const int64_t* bytes, uint32_t n, int64_
  * domain d are used[dom_off[d] .. dom_off[d+1]); out[d] = lowest multiple of step below limit not in them, -1 if none. */
 int  dra_imex_offsets_batch(dra_ctx* ctx, const int32_t* used, const uint32_t* dom_off, uint32_t n_dom,
                             int32_t step, int32_t limit, int32_t* out);
+
+/* ---- resident mode (DRA_CFG_RESIDENT) ------------------------------------------------------------------------------
+ * Optional explicit control: start the resident kernel now (the first eligible dra_allocate_batch would), stop it (every
+ * other entry point of the context does so implicitly before it runs).  dra_serve_batches: batches it has answered. */
+int  dra_serve_start(dra_ctx* ctx);
+int  dra_serve_stop(dra_ctx* ctx);
+uint64_t dra_serve_batches(const dra_ctx* ctx);
 
 /* ---- host memory + instrumentation ---------------------------------------------------------------- */
 

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libdra_alloc.so")
 
 OK, E_INVAL, E_CUDA, E_NCCL, E_NOMEM, E_STATE = 0, -1, -2, -3, -4, -5
-CFG_USE_GRAPH, CFG_NO_FUSED, CFG_NO_DIRECT = 0x1, 0x2, 0x4
+CFG_USE_GRAPH, CFG_NO_FUSED, CFG_NO_DIRECT, CFG_RESIDENT = 0x1, 0x2, 0x4, 0x8
 F_NODE_SORTED, F_FRESH_INVENTORY, F_EXHAUSTIVE = 0x1, 0x2, 0x4
 
 
@@ -63,6 +63,9 @@ SYMBOLS = {
     "dra_allocate_batch_global_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32]),
     "dra_mps_limits_batch": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "dra_imex_offsets_batch": (_i32, [_vp, _vp, _vp, _u32, C.c_int32, C.c_int32, _vp]),
+    "dra_serve_start": (_i32, [_vp]),
+    "dra_serve_stop": (_i32, [_vp]),
+    "dra_serve_batches": (_u64, [_vp]),
     "dra_host_alloc": (_vp, [C.c_size_t]),
     "dra_host_free": (None, [_vp]),
     "dra_launch_count": (_u64, [_vp]),
@@ -346,6 +349,16 @@ class Context:
         blob = b"".join(handles)
         buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
         self._check(self._lib.dra_peer_import(self._h, C.cast(buf, C.c_void_p)))
+
+    # -- resident mode ----------------------------------------------------------------------------------
+    def serve_start(self) -> None:
+        self._check(self._lib.dra_serve_start(self._h))
+
+    def serve_stop(self) -> None:
+        self._check(self._lib.dra_serve_stop(self._h))
+
+    def serve_batches(self) -> int:
+        return int(self._lib.dra_serve_batches(self._h))
 
     # -- instrumentation ------------------------------------------------------------------------------
     def launch_count(self) -> int:

@@ -122,6 +122,15 @@ struct dra_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
 
+    // resident mode (k_serve): the single-launch kernel stays up and takes batches by doorbell
+    bool serve_on = false;
+    cudaStream_t serve_stream = nullptr;
+    ServeCmd* h_cmd = nullptr; ServeCmd* h_cmd_dev = nullptr;          // mapped host memory (one cache line)
+    volatile uint32_t* h_stat = nullptr; uint32_t* h_stat_dev = nullptr;
+    uint32_t* d_go = nullptr;
+    uint32_t serve_seq = 0, serve_cap = 0; size_t serve_smem = 0; uint64_t serve_epoch = 0;
+    uint64_t serve_batches = 0;
+
     // CUDA-graph replay of the host-buffer Allocate call
     struct GraphKeyT { const void* c; const void* o; void* d; uint32_t n_claim, n_out, flags; uint64_t epoch;
                        bool operator==(const GraphKeyT& k) const { return c == k.c && o == k.o && d == k.d && n_claim == k.n_claim && n_out == k.n_out && flags == k.flags && epoch == k.epoch && c != nullptr; } };
@@ -434,13 +443,13 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         }
         a.claims = d_claims; a.out_off = d_out_off; a.n_claim = n_claim;
         if (getenv("DRA_TIMELINE")) {           // instrumentation only: per-CTA clock stamps of the last fused launch
-            if (ctx->tl_cap < (size_t)(n_node + 16) * 8) {
+            if (ctx->tl_cap < (size_t)(2 * n_node + 24) * 8) {
                 if (ctx->d_timeline) CU(cudaFree(ctx->d_timeline));
-                ctx->tl_cap = (size_t)(n_node + 16) * 8 + 64;
+                ctx->tl_cap = (size_t)(2 * n_node + 24) * 8 + 64;
                 CU(cudaMalloc((void**)&ctx->d_timeline, ctx->tl_cap * 8));
             }
             CU(cudaMemsetAsync(ctx->d_timeline, 0, ctx->tl_cap * 8, ctx->stream));
-            a.timeline = ctx->d_timeline; ctx->tl_n = (n_node + 3) * 8;
+            a.timeline = ctx->d_timeline; ctx->tl_n = (2 * n_node + 6) * 8;
         }
         prof.skip_to(3);
         // grid = one CTA per node + one CTA for the claims that name no node (+ padding to whole clusters)
@@ -532,8 +541,109 @@ int raise_smem_limits(dra_ctx* ctx, int optin) {
     if ((rc = raise_one(ctx, k_bucket_small, optin))) return rc;
     if ((rc = raise_one(ctx, k_bucket_hist8, optin))) return rc;
     if ((rc = raise_one(ctx, k_bucket_hist, optin))) return rc;
+    if ((rc = raise_one(ctx, k_serve<FUSED_NW>, optin))) return rc;
     return DRA_OK;
 }
+
+// ---- resident mode -----------------------------------------------------------------------------------------------
+// Stops the resident kernel (if any): EXIT command, then wait for the kernel to leave.  Every entry point that launches
+// other work or touches device state calls this first — the resident kernel owns the SMs' shared memory while it runs.
+int serve_stop(dra_ctx* ctx) {
+    if (!ctx->serve_on) return DRA_OK;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->h_stat[1] != 2u) {
+        ServeCmd* c = ctx->h_cmd;
+        c->n_claim = 0; c->n_out = 0; c->flags = SERVE_EXIT; c->claims = 0; c->out_off = 0; c->out = 0;
+        __atomic_store_n(&c->seq, ctx->serve_seq + 1u, __ATOMIC_RELEASE);
+    }
+    CU(cudaStreamSynchronize(ctx->serve_stream));
+    ctx->serve_on = false;
+    ctx->serve_seq += 1;                        // the EXIT consumed a sequence number (or none was taken: harmless gap)
+    return DRA_OK;
+}
+
+// largest claim count whose staged layout fits the single-launch kernel's shared memory
+uint32_t serve_capacity() {
+    uint32_t lo = 256, hi = FUSED_NW * FU_PIECE * FU_MAXPIECE;
+    while (lo < hi) { const uint32_t mid = (lo + hi + 1) / 2; if (fused_smem_bytes(mid, FUSED_NW, true) <= 225 * 1024) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+int serve_start(dra_ctx* ctx) {
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->serve_stream) CU(cudaStreamCreateWithFlags(&ctx->serve_stream, cudaStreamNonBlocking));
+    if (!ctx->h_cmd) {
+        void* p = nullptr;
+        CU(cudaHostAlloc(&p, 256, cudaHostAllocMapped));
+        memset(p, 0, 256);
+        ctx->h_cmd = (ServeCmd*)p; ctx->h_stat = (volatile uint32_t*)((uint8_t*)p + 128);
+        void* dp = nullptr;
+        CU(cudaHostGetDevicePointer(&dp, p, 0));
+        ctx->h_cmd_dev = (ServeCmd*)dp; ctx->h_stat_dev = (uint32_t*)((uint8_t*)dp + 128);
+        CU(cudaMalloc((void**)&ctx->d_go, 256)); CU(cudaMemset(ctx->d_go, 0, 256));
+    }
+    if (!ctx->d_gbar) { CU(cudaMalloc((void**)&ctx->d_gbar, 64)); CU(cudaMemset(ctx->d_gbar, 0, 64)); }
+    int rc = upload_table(ctx);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));                  // earlier work of this context is done before the kernel takes over
+    ctx->serve_cap = serve_capacity();
+    ctx->serve_smem = fused_smem_bytes(ctx->serve_cap, FUSED_NW, true);
+    if ((rc = ensure_batch(ctx, ctx->serve_cap, ctx->serve_cap * 2, true))) return rc;
+    ServeArgs sa; memset(&sa, 0, sizeof sa);
+    PackArgs& a = sa.base;
+    a.inv_dst = ctx->d_inv_live; a.inv_src = ctx->d_inv_live; a.node_off = ctx->d_node_off; a.tbl = ctx->d_tbl;
+    a.out = ctx->d_out; a.n_node = ctx->n_node; a.err = err_of(ctx); a.sel = sel_of(ctx);
+    a.claims = ctx->d_claims;
+    a.dio.d_claims = ctx->d_claims; a.dio.d_out_off = ctx->d_out_off; a.dio.gbar = ctx->d_gbar;
+    sa.inv_pristine = ctx->d_inv_pristine;
+    sa.h_cmd = ctx->h_cmd_dev; sa.h_stat = ctx->h_stat_dev; sa.d_go = ctx->d_go;
+    sa.first_seq = ctx->serve_seq + 1; sa.cap_claims = ctx->serve_cap;
+    static const long long idle_ms = getenv("DRA_SERVE_IDLE_MS") ? atoll(getenv("DRA_SERVE_IDLE_MS")) : 20;
+    sa.idle_cycles = std::max(1ll, idle_ms) * 1900000ll;
+    ctx->h_stat[1] = 0; ctx->h_stat[2] = 0;
+    CU(cudaMemsetAsync(ctx->d_go, 0, 256, ctx->serve_stream));
+    cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(ctx->n_node + 1); lc.blockDim = dim3(FUSED_NW * 32); lc.dynamicSmemBytes = ctx->serve_smem; lc.stream = ctx->serve_stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&lc, k_serve<FUSED_NW>, sa));
+    ctx->launches += 1;
+    ctx->serve_on = true; ctx->serve_epoch = ctx->state_epoch;
+    return DRA_OK;
+}
+
+// one batch through the resident kernel; *took = false when the kernel had gone idle before it saw the doorbell
+int serve_call(dra_ctx* ctx, const void* src_c, uint32_t n_claim, const void* src_o, void* dst_o, uint32_t n_out, uint32_t flags) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (!ctx->serve_on || ctx->h_stat[1] == 2u || ctx->serve_epoch != ctx->state_epoch) {
+            int rc = serve_stop(ctx);
+            if (rc) return rc;
+            if ((rc = serve_start(ctx))) return rc;
+        }
+        const uint32_t seq = ctx->serve_seq + 1u;
+        ServeCmd* c = ctx->h_cmd;
+        c->n_claim = n_claim; c->n_out = n_out; c->flags = flags & DRA_F_FRESH_INVENTORY;
+        c->claims = (unsigned long long)(uintptr_t)src_c; c->out_off = (unsigned long long)(uintptr_t)src_o; c->out = (unsigned long long)(uintptr_t)dst_o;
+        __atomic_store_n(&c->seq, seq, __ATOMIC_RELEASE);                  // the doorbell
+        uint64_t spins = 0;
+        bool done = false, gone = false;
+        while (true) {
+            if (__atomic_load_n((const uint32_t*)&ctx->h_stat[0], __ATOMIC_ACQUIRE) == seq) { done = true; break; }
+            if ((++spins & 0xFFu) == 0) {
+                if (ctx->h_stat[1] == 2u) { gone = __atomic_load_n((const uint32_t*)&ctx->h_stat[0], __ATOMIC_ACQUIRE) != seq; if (gone) break; done = true; break; }
+                if (spins > (1ull << 31)) return fail(ctx, DRA_E_CUDA, "resident kernel does not answer");
+            }
+        }
+        if (done) { ctx->serve_seq = seq; ctx->serve_batches++; return DRA_OK; }
+        // the kernel left (idle time-out) before it saw this doorbell: start it again and ring once more
+        CU(cudaStreamSynchronize(ctx->serve_stream));
+        ctx->serve_on = false;
+    }
+    return fail(ctx, DRA_E_CUDA, "resident kernel keeps leaving before it takes the batch");
+}
+
+#define QUIESCE() do { int q_ = serve_stop(ctx); if (q_) return q_; } while (0)
 }  // namespace
 
 extern "C" {
@@ -589,6 +699,10 @@ int dra_ctx_create(const dra_cfg* cfg, dra_ctx** out) {
 void dra_ctx_destroy(dra_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    (void)serve_stop(c);
+    if (c->serve_stream) cudaStreamDestroy(c->serve_stream);
+    if (c->h_cmd) cudaFreeHost(c->h_cmd);
+    if (c->d_go) cudaFree(c->d_go);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->comm) { std::lock_guard<std::mutex> lk(g_nccl_mu); if (g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm); }
@@ -612,6 +726,7 @@ void dra_ctx_destroy(dra_ctx* c) {
 
 int dra_set_placement_table(dra_ctx* ctx, uint32_t model, const dra_profile_tbl* tbl) {
     if (!ctx || !tbl) return DRA_E_INVAL;
+    QUIESCE();
     if (model >= DRA_MAX_MODELS) return fail(ctx, DRA_E_INVAL, "model %u >= %u", model, DRA_MAX_MODELS);
     for (uint32_t p = 0; p < DRA_MAX_PROFILES; ++p) {
         const dra_prof_ent& e = tbl->ent[p];
@@ -628,6 +743,7 @@ int dra_set_placement_table(dra_ctx* ctx, uint32_t model, const dra_profile_tbl*
 
 int dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu, const uint32_t* node_off, uint32_t n_node) {
     if (!ctx || !node_off || (n_gpu && !gpus)) return DRA_E_INVAL;
+    QUIESCE();
     CU(cudaSetDevice(ctx->device));
     if (node_off[0] != 0 || node_off[n_node] != n_gpu) return fail(ctx, DRA_E_INVAL, "node_off must span [0, n_gpu]");
     for (uint32_t n = 0; n < n_node; ++n) {
@@ -667,6 +783,7 @@ int dra_set_inventory(dra_ctx* ctx, const dra_gpu_rec* gpus, uint32_t n_gpu, con
 
 int dra_set_gpu_attrs(dra_ctx* ctx, const dra_gpu_attr* attrs, uint32_t n_gpu) {
     if (!ctx || (n_gpu && !attrs)) return DRA_E_INVAL;
+    QUIESCE();
     static_assert(sizeof(dra_gpu_attr) == 16 && sizeof(dra_selector) == 64, "selector record layout");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -683,6 +800,7 @@ int dra_set_gpu_attrs(dra_ctx* ctx, const dra_gpu_attr* attrs, uint32_t n_gpu) {
 
 int dra_set_selectors(dra_ctx* ctx, const dra_selector* sels, uint32_t n_sel) {
     if (!ctx || (n_sel && !sels)) return DRA_E_INVAL;
+    QUIESCE();
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_sels) { CU(cudaFree(ctx->d_sels)); ctx->d_sels = nullptr; }
@@ -698,6 +816,7 @@ int dra_set_selectors(dra_ctx* ctx, const dra_selector* sels, uint32_t n_sel) {
 
 int dra_get_inventory(dra_ctx* ctx, dra_gpu_rec* gpus, uint32_t n_gpu) {
     if (!ctx || !gpus) return DRA_E_INVAL;
+    QUIESCE();
     if (n_gpu != ctx->n_gpu) return fail(ctx, DRA_E_INVAL, "n_gpu %u != inventory size %u", n_gpu, ctx->n_gpu);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -707,6 +826,7 @@ int dra_get_inventory(dra_ctx* ctx, dra_gpu_rec* gpus, uint32_t n_gpu) {
 
 int dra_reset_inventory(dra_ctx* ctx) {
     if (!ctx) return DRA_E_INVAL;
+    QUIESCE();
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "no inventory");
     CU(cudaSetDevice(ctx->device));
     if (ctx->n_gpu) CU(cudaMemcpyAsync(ctx->d_inv_live, ctx->d_inv_pristine, (size_t)ctx->n_gpu * 16, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -715,6 +835,7 @@ int dra_reset_inventory(dra_ctx* ctx) {
 
 int dra_ctx_sync(dra_ctx* ctx) {
     if (!ctx) return DRA_E_INVAL;
+    QUIESCE();
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     collect_timings(ctx, 5);
@@ -724,6 +845,7 @@ int dra_ctx_sync(dra_ctx* ctx) {
 int dra_allocate_batch_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                               dra_out_rec* d_out, uint32_t n_out, uint32_t flags) {
     if (!ctx || (n_claim && (!d_claims || !d_out))) return DRA_E_INVAL;
+    QUIESCE();
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_batch(ctx, n_claim, n_out, false);
     if (rc) return rc;
@@ -752,6 +874,34 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
     if (rb && !direct && (rc = grow_pinned(ctx, ctx->h_out, ctx->h_out_cap, rb))) return rc;
     void* dst_o = direct ? (void*)out : (void*)ctx->h_out;
 
+    // Resident mode (DRA_CFG_RESIDENT): the kernel is already up — write the command, ring the doorbell, spin on the
+    // completion word.  Same eligibility as direct host I/O below; anything else stops the resident kernel first.
+    {
+        bool ok = (ctx->cfg_flags & DRA_CFG_RESIDENT) && ctx->coop_ok && n_claim && rb && !ctx->profiling && !getenv("DRA_TIMELINE") &&
+                  !(flags & ~DRA_F_FRESH_INVENTORY) && (int)(ctx->n_node + 1) <= ctx->n_sm && ctx->d_inv_live &&
+                  ((uintptr_t)src_c & 15) == 0 && ((uintptr_t)dst_o & 15) == 0 && (!src_o || ((uintptr_t)src_o & 3) == 0);
+        if (ok) {
+            if (!ctx->serve_cap) ctx->serve_cap = serve_capacity();
+            ok = n_claim <= ctx->serve_cap && n_out <= 2 * ctx->serve_cap;
+        }
+        if (ok) {
+            const void* hp[3] = {src_c, src_o, dst_o};
+            for (int k = 0; k < 3 && ok; ++k) {
+                if (!hp[k] || ctx->dio_seen[k] == hp[k]) continue;
+                void* dp = nullptr;
+                if (cudaHostGetDevicePointer(&dp, const_cast<void*>(hp[k]), 0) != cudaSuccess || dp != hp[k]) { (void)cudaGetLastError(); ok = false; }
+                else ctx->dio_seen[k] = hp[k];
+            }
+        }
+        if (ok) {
+            rc = serve_call(ctx, src_c, n_claim, src_o, dst_o, n_out, flags);
+            if (rc) return rc;
+            if ((rc = check_err(ctx))) return rc;
+            if (rb && !direct) memcpy(out, ctx->h_out, rb);
+            return DRA_OK;
+        }
+        QUIESCE();
+    }
     // Direct host I/O: when the batch takes the single-launch kernel with the claim array staged in shared memory
     // and all its CTAs can be resident at once, the kernel itself reads the claims from the (pinned, device-mapped)
     // host buffer and writes the OutRecs back there — no copy-engine transfers, no graph, one cooperative launch.
@@ -845,6 +995,7 @@ int dra_allocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_cla
 int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* pod_off, uint32_t n_pod,
                          const uint32_t* cand_nodes, const uint32_t* cand_off, uint8_t* suitable_bits, uint32_t flags) {
     if (!ctx || !pod_off || (n_claim && !claims)) return DRA_E_INVAL;
+    QUIESCE();
     if (flags & ~DRA_F_EXHAUSTIVE) return fail(ctx, DRA_E_INVAL, "dra_unsuitable_batch: unknown flags 0x%x", flags);
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
     if (pod_off[0] != 0 || pod_off[n_pod] != n_claim) return fail(ctx, DRA_E_INVAL, "pod_off must span [0, n_claim]");
@@ -944,6 +1095,7 @@ int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
 int dra_allocate_pods_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* pod_off, uint32_t n_pod,
                             const uint32_t* out_off, dra_out_rec* out, uint32_t n_out, uint32_t flags) {
     if (!ctx || !pod_off || (n_claim && (!claims || !out))) return DRA_E_INVAL;
+    QUIESCE();
     if (flags & ~(DRA_F_EXHAUSTIVE | DRA_F_FRESH_INVENTORY)) return fail(ctx, DRA_E_INVAL, "dra_allocate_pods_batch: unknown flags 0x%x", flags);
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
     if (pod_off[0] != 0 || pod_off[n_pod] != n_claim) return fail(ctx, DRA_E_INVAL, "pod_off must span [0, n_claim]");
@@ -1007,6 +1159,7 @@ int dra_allocate_pods_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t 
 int dra_deallocate_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_claim, const uint32_t* out_off,
                          const dra_out_rec* out, uint32_t n_out) {
     if (!ctx || (n_claim && (!claims || !out))) return DRA_E_INVAL;
+    QUIESCE();
     if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
     if (!n_claim) return DRA_OK;
     CU(cudaSetDevice(ctx->device));
@@ -1190,6 +1343,7 @@ int dra_comm_init_local(dra_ctx* ctx, int rank, int world) {
 int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                                      dra_out_rec* d_out_all, uint32_t n_out, uint32_t n_per_rank, uint32_t flags) {
     if (!ctx || (n_claim && !d_claims)) return DRA_E_INVAL;
+    QUIESCE();
     if (!ctx->comm && !ctx->peer_ready) return fail(ctx, DRA_E_STATE, "dra_comm_init has not been called");
     if (!d_out_all && !ctx->peer_ready) return fail(ctx, DRA_E_INVAL, "d_out_all may be NULL only with the peer all-gather set up");
     if (n_out > n_per_rank) return fail(ctx, DRA_E_INVAL, "n_out %u > n_per_rank %u", n_out, n_per_rank);
@@ -1239,6 +1393,7 @@ int dra_set_shard(dra_ctx* ctx, uint32_t node_lo, uint32_t node_hi, int take_str
 int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                                      uint32_t n_out, uint32_t flags) {
     if (!ctx || (n_claim && !d_claims)) return DRA_E_INVAL;
+    QUIESCE();
     if (!ctx->shard_on) return fail(ctx, DRA_E_STATE, "dra_set_shard has not been called");
     if (flags & ~DRA_F_FRESH_INVENTORY) return fail(ctx, DRA_E_INVAL, "dra_allocate_batch_global_device: unsupported flags 0x%x", flags);
     if (n_claim > (1u << 26) || n_out > (1u << 26)) return fail(ctx, DRA_E_INVAL, "batch too large for the sharded call (2^26)");
@@ -1343,6 +1498,7 @@ int dra_gather_table(dra_ctx* ctx, const dra_out_rec** d_table, uint32_t* n_per_
 
 int dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec) {
     if (!ctx || !out_all) return DRA_E_INVAL;
+    QUIESCE();
     if (!ctx->gather_table) return fail(ctx, DRA_E_STATE, "no gather has run");
     if (n_rec > (ctx->gather_len ? ctx->gather_len : (uint32_t)ctx->world * ctx->gather_n_per)) return fail(ctx, DRA_E_INVAL, "n_rec %u exceeds the table", n_rec);
     CU(cudaSetDevice(ctx->device));
@@ -1360,6 +1516,7 @@ int dra_gather_read(dra_ctx* ctx, dra_out_rec* out_all, uint32_t n_rec) {
 // ---- adjacent integer searches, batched ------------------------------------------------
 int dra_mps_limits_batch(dra_ctx* ctx, const int64_t* bytes, uint32_t n, int64_t* mib, uint8_t* valid) {
     if (!ctx || (n && (!bytes || !mib || !valid))) return DRA_E_INVAL;
+    QUIESCE();
     if (!n) return DRA_OK;
     CU(cudaSetDevice(ctx->device));
     void *d_b = nullptr, *d_m = nullptr, *d_v = nullptr;
@@ -1377,6 +1534,7 @@ int dra_mps_limits_batch(dra_ctx* ctx, const int64_t* bytes, uint32_t n, int64_t
 
 int dra_imex_offsets_batch(dra_ctx* ctx, const int32_t* used, const uint32_t* dom_off, uint32_t n_dom, int32_t step, int32_t limit, int32_t* out) {
     if (!ctx || !dom_off || (n_dom && !out) || step <= 0 || limit < 0) return DRA_E_INVAL;
+    QUIESCE();
     if (!n_dom) return DRA_OK;
     const uint32_t n_used = dom_off[n_dom];
     if (n_used && !used) return DRA_E_INVAL;
@@ -1394,6 +1552,18 @@ int dra_imex_offsets_batch(dra_ctx* ctx, const int32_t* used, const uint32_t* do
     if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "dra_imex_offsets_batch: %s", cudaGetErrorString(e));
     return DRA_OK;
 }
+
+// ---- resident mode ---------------------------------------------------------------------------------------------------
+int dra_serve_start(dra_ctx* ctx) {
+    if (!ctx) return DRA_E_INVAL;
+    if (!ctx->d_inv_live) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
+    if (!ctx->coop_ok || (int)(ctx->n_node + 1) > ctx->n_sm) return fail(ctx, DRA_E_STATE, "resident mode needs every node's CTA resident at once: %u nodes, %d SMs", ctx->n_node, ctx->n_sm);
+    int rc = serve_stop(ctx);
+    if (rc) return rc;
+    return serve_start(ctx);
+}
+int dra_serve_stop(dra_ctx* ctx) { if (!ctx) return DRA_E_INVAL; return serve_stop(ctx); }
+uint64_t dra_serve_batches(const dra_ctx* ctx) { return ctx ? ctx->serve_batches : 0; }
 
 // ---- host memory + instrumentation -----------------------------------------------------------------
 
@@ -1418,6 +1588,7 @@ namespace { __global__ void k_noop(int x) { extern __shared__ uint8_t sm[]; if (
 // Instrumentation: enqueue an empty kernel with the given shape (calibrates the launch floor of the box).
 int dra_debug_noop(dra_ctx* ctx, uint32_t grid, uint32_t block, uint32_t smem) {
     if (!ctx) return DRA_E_INVAL;
+    QUIESCE();
     CU(cudaSetDevice(ctx->device));
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_noop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_noop<<<grid, block, smem, ctx->stream>>>(0);

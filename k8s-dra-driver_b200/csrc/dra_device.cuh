@@ -1054,6 +1054,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ void mbar_init_a(uint32_t addr, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval_a(uint32_t addr) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
     uint32_t ok;
     do {
@@ -1513,6 +1516,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
 }
 #define DRA_DSTAMP(k) do { if (a.timeline && blockIdx.x == 0 && threadIdx.x == 0) a.timeline[(a.n_node + 2) * 8 + (k)] = globaltimer_ns(); } while (0)
+#define DRA_TSTAMP(k) do { if (a.timeline && threadIdx.x == 0) a.timeline[(a.n_node + 4) * 8 + blockIdx.x * 8 + (k)] = globaltimer_ns(); } while (0)
 #define DRA_STAMP(k) do { if (a.timeline && threadIdx.x == 0) a.timeline[blockIdx.x * 8 + (k)] = (k) == 0 ? globaltimer_ns() : (unsigned long long)clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -1554,35 +1558,52 @@ __device__ __forceinline__ void grid_barrier(uint32_t* gbar, uint32_t n_cta, con
 
 // CL = thread-block cluster size (1 or 8).  With CL = 8 the staged claim array is fetched from L2 ONCE per
 // cluster: CTA r of the cluster loads pieces r, r+8, ... and TMA-multicasts each into all 8 CTAs.
+// The body of the single-launch kernel: one batch.  k_fused runs it once; k_serve (resident mode) runs it once per doorbell
+// (`again`: the shared-memory barriers of the previous batch are invalidated first).
+// What differs from batch to batch (resident mode keeps everything else in the kernel's parameter space)
+struct Batch {
+    uint32_t n_claim, n_out, have_off, serve;
+    const uint4* inv_src;
+    const uint32_t* out_off;
+    const uint4* h_claims; const uint32_t* h_out_off; uint2* h_out;
+};
+
 template <int NW, bool STAGE, int CL>
-__global__ void __launch_bounds__(NW * 32, 1)
-k_fused(const PackArgs a) {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
+__device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uint8_t* dyn_smem, const bool again) {
     static_assert(CL == 1 || STAGE, "clusters only make sense with the staged claim array");
-    DRA_STAMP(0); DRA_STAMP(1);
+    DRA_STAMP(0); DRA_STAMP(1); DRA_TSTAMP(0);
     const uint32_t sbase = smem_base(dyn_smem);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t node = blockIdx.x;
     const bool has_node = node < a.n_node;       // CTA n_node handles claims that name no node; later CTAs pad the cluster
     const uint32_t tbar = sbase + FU_TBAR, ibar = sbase + FU_IBAR;
     const uint32_t list_addr = sbase + FU_LIST + (STAGE ? (uint32_t)NW * FU_MAXPIECE * 8u : 0u);
-    const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(a.n_claim, NW, STAGE) + 15u) & ~15u) : 0u;
+    const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(b.n_claim, NW, STAGE) + 15u) & ~15u) : 0u;
     const uint32_t sbar = sbase + FU_LIST;       // STAGE: one mbarrier per 4 KiB piece of the claim array
     // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
     uint32_t g0 = 0, g1 = 0;
     if (has_node) { g0 = __ldg(&a.node_off[node]); g1 = __ldg(&a.node_off[node + 1]); }
     // barrier init spread over the threads (one mbarrier.init each), then one fence + sync
+    if (again) {                                   // resident mode: the previous batch's barriers are dead objects now
+        __syncthreads();
+        if (threadIdx.x == 0) { mbar_inval_a(tbar); mbar_inval_a(ibar); }
+        if (STAGE && threadIdx.x < NW * FU_MAXPIECE) mbar_inval_a(sbar + threadIdx.x * 8);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) { mbar_init_a(tbar, 1); mbar_init_a(ibar, 1); }
-    if (STAGE) { const uint32_t npt_ = (a.n_claim + FU_PIECE - 1) / FU_PIECE; if (threadIdx.x < npt_) mbar_init_a(sbar + threadIdx.x * 8, 1); }
+    if (STAGE) {                                   // (resident mode initialises all of them: the next batch may be larger)
+        const uint32_t npt_ = again || b.serve ? NW * FU_MAXPIECE : (b.n_claim + FU_PIECE - 1) / FU_PIECE;
+        if (threadIdx.x < npt_) mbar_init_a(sbar + threadIdx.x * 8, 1);
+    }
     mbar_fence_init();
     __syncthreads();
     if (threadIdx.x == 0) tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
     const uint32_t ng = g1 - g0;
-    if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, a.inv_src + g0, ng * 16u, ibar);
-    // sharded call: the claim list was compacted on the device by the kernel before this one; a.n_claim is its capacity
+    if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, b.inv_src + g0, ng * 16u, ibar);
+    // sharded call: the claim list was compacted on the device by the kernel before this one; b.n_claim is its capacity
     if (a.n_dev) pdl_wait();                                 // (launched as a programmatic dependent of the compaction)
-    const uint32_t n_claim = a.n_dev ? min(a.n_claim, __ldcg(a.n_dev)) : a.n_claim;
-    if (a.n_dev && __ldcg(a.n_dev) > a.n_claim) {            // laid out for fewer claims: touch nothing, tell everybody
+    const uint32_t n_claim = a.n_dev ? min(b.n_claim, __ldcg(a.n_dev)) : b.n_claim;
+    if (a.n_dev && __ldcg(a.n_dev) > b.n_claim) {            // laid out for fewer claims: touch nothing, tell everybody
         if (blockIdx.x == 0) {
             if (threadIdx.x == 0) a.err.set(ERR_SHARD_PLAN);
             if (a.peer.world) { pkt_send_header(a.peer, threadIdx.x, 0xFFFFFFFFu); if (threadIdx.x == 32) a.peer.cursor[a.peer.parity ^ 1u] = 0; }
@@ -1590,15 +1611,15 @@ k_fused(const PackArgs a) {
         return;
     }
 
-    if (STAGE && CL == 1 && a.dio.h_claims) {
+    if (STAGE && CL == 1 && b.h_claims) {
         // direct ingest: one 16-byte load from the caller's pinned buffer per thread (a single PCIe round trip for
         // the whole grid), stored to the device copy that everybody's bulk copies below read from L2.
         // (Per-piece ready flags instead of the grid barrier were tried: slower, 8.1 vs 5.8 us to the first bulk
         // copy — every producer then pays its own fence on the critical path.)
         DRA_DSTAMP(0);
         const uint32_t nthr = gridDim.x * (NW * 32), t0 = blockIdx.x * (NW * 32) + threadIdx.x;
-        for (uint32_t i = t0; i < a.n_claim; i += nthr) a.dio.d_claims[i] = __ldcs(a.dio.h_claims + i);
-        if (a.dio.h_out_off) for (uint32_t i = t0; i < a.n_claim; i += nthr) a.dio.d_out_off[i] = __ldcs(a.dio.h_out_off + i);
+        for (uint32_t i = t0; i < b.n_claim; i += nthr) a.dio.d_claims[i] = __ldcs(b.h_claims + i);
+        if (b.h_out_off) for (uint32_t i = t0; i < b.n_claim; i += nthr) a.dio.d_out_off[i] = __ldcs(b.h_out_off + i);
         DRA_DSTAMP(1);
         grid_barrier(a.dio.gbar, gridDim.x, a.err);
         asm volatile("fence.proxy.async;" ::: "memory");       // generic-proxy stores (other SMs) -> bulk-copy reads
@@ -1631,9 +1652,9 @@ k_fused(const PackArgs a) {
         x.lane = lane; x.ltmask = lanemask_lt();
         x.live_addr = sbase + FU_LIVE; x.tbl_addr = sbase + FU_TBL;
         x.tbl_ptr = reinterpret_cast<const uint32_t*>(dyn_smem + FU_TBL);
-        x.have_off = a.have_off != 0;
+        x.have_off = b.have_off != 0;
         x.sc = a.sel;
-        x.sink = OutSink{a.out, a.n_out, a.err, lane};
+        x.sink = OutSink{a.out, b.n_out, a.err, lane};
         x.g0 = g0;
         mbar_wait_a(tbar, 0);
         if (ng) { mbar_wait_a(ibar, 0); if (lane < ng) rec = lds128(sbase + FU_INV + lane * 16); }
@@ -1698,7 +1719,7 @@ k_fused(const PackArgs a) {
     DRA_STAMP(4);
 
     IdxGet<NW> get;
-    get.claims = a.claims; get.out_off = a.out_off; get.list_addr = list_addr; get.chunk = chunk;
+    get.claims = a.claims; get.out_off = b.out_off; get.list_addr = list_addr; get.chunk = chunk;
     get.stage_addr = stage_addr;
     uint32_t cnt = 0;
     #pragma unroll
@@ -1708,17 +1729,17 @@ k_fused(const PackArgs a) {
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
             const uint4 c = STAGE ? lds128(stage_addr + (i << 4)) : __ldcg(&a.claims[i]);
-            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i;
+            const uint32_t dst = b.out_off ? __ldcg(&b.out_off[i]) : i;
             const uint32_t kind = c.x & 0xFFu;
             const uint32_t op = kind == DRA_KIND_GPU ? DRA_PROFILE_GPU : kind == DRA_KIND_SHARED ? DRA_PROFILE_SHARED : ((c.x >> 8) & 0xFFu);
-            if (dst < a.n_out) a.out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
+            if (dst < b.n_out) a.out[dst] = make_uint2(DRA_GPU_NONE, meta(0, 0, op, DRA_ST_INVALID));
             else a.err.set(ERR_OUT_RANGE);
         }
     }
     // ---- pack: warp 0 ----------------------------------------------------------------------------------
     if (wid == 0 && has_node) {
         if (cnt == 0) {
-            if (a.inv_src != a.inv_dst && lane < ng) a.inv_dst[g0 + lane] = __ldg(&a.inv_src[g0 + lane]);
+            if (b.inv_src != a.inv_dst && lane < ng) a.inv_dst[g0 + lane] = __ldg(&b.inv_src[g0 + lane]);
         } else {
             // the first segment's claims are requested before waiting for the table / inventory
             auto fetch = [&](uint32_t seg, uint4& c, bool& present) {
@@ -1752,7 +1773,7 @@ k_fused(const PackArgs a) {
         }
     }
     if (CL > 1) cluster_wait();                    // nobody leaves while a cluster peer may still be receiving multicasts
-    if (STAGE && CL == 1 && a.dio.h_claims) {
+    if (STAGE && CL == 1 && b.h_claims) {
         // direct egress: when every CTA's OutRecs are in the device buffer, the grid writes them to the caller's
         // pinned buffer as coalesced 16-byte stores (a scattered 8-byte store per record is what makes plain
         // zero-copy output slow: profiles/e2e_parts_r01e.txt)
@@ -1760,11 +1781,11 @@ k_fused(const PackArgs a) {
         grid_barrier(a.dio.gbar, gridDim.x, a.err);
         DRA_DSTAMP(4);
         const uint32_t nthr = gridDim.x * (NW * 32), t0 = blockIdx.x * (NW * 32) + threadIdx.x;
-        const uint32_t n16 = a.n_out >> 1;
+        const uint32_t n16 = b.n_out >> 1;
         const uint4* src = reinterpret_cast<const uint4*>(a.out);
-        uint4* dst = reinterpret_cast<uint4*>(a.dio.h_out);
+        uint4* dst = reinterpret_cast<uint4*>(b.h_out);
         for (uint32_t i = t0; i < n16; i += nthr) __stcs(dst + i, __ldcg(src + i));
-        if ((a.n_out & 1u) && t0 == 0) a.dio.h_out[a.n_out - 1] = __ldcg(a.out + a.n_out - 1);
+        if ((b.n_out & 1u) && t0 == 0) b.h_out[b.n_out - 1] = __ldcg(a.out + b.n_out - 1);
         DRA_DSTAMP(5);
         return;
     }
@@ -1774,6 +1795,7 @@ k_fused(const PackArgs a) {
     // 1. every CTA sends the OutRecs of ITS node's claims as packets into a contiguous range of this rank's slice at
     //    every peer; 2. every CTA then polls its share of the peers' slices in local memory and fills the table.
     __syncthreads();                                   // warp 0's OutRecs are visible to the whole CTA
+    DRA_TSTAMP(1);
     const PktGather& pg = a.peer;
     __shared__ uint32_t pk_total_s, pk_base_s, pk_next_s;
     if (threadIdx.x == 0) { pk_total_s = 0; pk_next_s = 0; }
@@ -1782,15 +1804,15 @@ k_fused(const PackArgs a) {
     // the claims this CTA answers for: its node's list, or (CTA n_node) the claims that name no node (one slot each)
     auto slots_of = [&](const uint4 c) -> uint32_t {
         const uint32_t kind = c.x & 0xFFu, count = c.x >> 16;
-        return (!stray_cta && kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u;
+        return (!stray_cta && kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, b.have_off != 0)) ? count : 1u;
     };
     auto claim_at = [&](uint32_t i) -> uint4 { return STAGE ? lds128(stage_addr + (i << 4)) : __ldcg(&a.claims[i]); };
     uint32_t mine = 0;
     if (has_node || stray_cta) {
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
-            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(claim_at(i));
-            if (!(dst > a.n_out || sl > a.n_out - dst)) mine += sl;
+            const uint32_t dst = b.out_off ? __ldcg(&b.out_off[i]) : i, sl = slots_of(claim_at(i));
+            if (!(dst > b.n_out || sl > b.n_out - dst)) mine += sl;
         }
     }
     mine = __reduce_add_sync(FULLMASK, mine);
@@ -1802,15 +1824,116 @@ k_fused(const PackArgs a) {
         const uint32_t base = pk_base_s;
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
-            const uint32_t dst = a.out_off ? __ldcg(&a.out_off[i]) : i, sl = slots_of(claim_at(i));
-            if (dst > a.n_out || sl > a.n_out - dst) continue;
+            const uint32_t dst = b.out_off ? __ldcg(&b.out_off[i]) : i, sl = slots_of(claim_at(i));
+            if (dst > b.n_out || sl > b.n_out - dst) continue;
             const uint32_t at = base + atomicAdd(&pk_next_s, sl);
             for (uint32_t s_ = 0; s_ < sl; ++s_)
                 if (at + s_ < pg.cap) pkt_send(pg, at + s_, __ldcg(a.out + dst + s_), pg.slot_base + dst + s_);
         }
     }
+    DRA_TSTAMP(2);
     pkt_finish_send(pg);                               // the last CTA to get here tells the peers how many packets went out
+    DRA_TSTAMP(3);
     pkt_receive(pg, blockIdx.x * (NW * 32) + threadIdx.x, gridDim.x * (NW * 32), a.err);
+    __syncthreads();
+    DRA_TSTAMP(4);
+}
+
+template <int NW, bool STAGE, int CL>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_fused(const PackArgs a) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const Batch b{a.n_claim, a.n_out, a.have_off, 0u, a.inv_src, a.out_off, a.dio.h_claims, a.dio.h_out_off, a.dio.h_out};
+    fused_body<NW, STAGE, CL>(a, b, dyn_smem, false);
+}
+
+// ---- resident mode: the kernel stays up and takes batches by DOORBELL ------------------------------------------------
+// of the 36.5 us a host call took, ~16 us were the cooperative launch and the stream synchronisation.
+// Here the kernel is launched once; a call is: the host writes a 64-byte command (sizes, flags, the pinned buffers) into
+// mapped host memory, then its sequence number; CTA 0 polls that word, relays the command through L2, every CTA runs
+// the batch body with direct host I/O (ingest -> barrier -> filter + pack -> barrier -> egress), and after a system fence
+// per CTA and a last grid barrier CTA 0 writes the sequence number into the host's completion word.  No launch, no
+// stream call, no driver call on the host at all.  The kernel leaves on an EXIT command or after `idle` cycles without
+// a doorbell (the host relaunches on demand), so it can never outlive its owner by more than that.
+struct ServeCmd {                 // one cache line of mapped host memory, written by the host
+    uint32_t seq, n_claim, n_out, flags;         // flags: DRA_F_FRESH_INVENTORY | SERVE_EXIT
+    unsigned long long claims, out_off, out;     // pinned host buffers of this batch (device-visible addresses)
+    unsigned long long pad[3];
+};
+constexpr uint32_t SERVE_EXIT = 0x80000000u;
+struct ServeArgs {
+    PackArgs base;                // inventory, table, node_off, err, selectors, device copies (dio.d_claims ...), dio.gbar
+    const uint4* inv_pristine;
+    const volatile ServeCmd* h_cmd;              // device view of the command line
+    volatile uint32_t* h_stat;                   // [0] completed seq, [1] state: 1 running, 2 exited, [2] exit reason
+    uint32_t* d_go;                              // device: [0] sequence relayed by CTA 0, [4..19] the command copy
+    uint32_t first_seq, cap_claims;
+    long long idle_cycles;
+};
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_serve(const ServeArgs s) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    __shared__ uint32_t cmd_s[12];
+    uint32_t seq = s.first_seq;
+    bool again = false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { s.h_stat[1] = 1u; __threadfence_system(); }
+    for (;;) {
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) {
+                // the doorbell: one 16-byte load of {seq, n_claim, n_out, flags} per poll
+                const long long t0 = clock64();
+                uint4 h; bool quit = false;
+                for (;;) {
+                    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(s.h_cmd) : "memory");
+                    if (h.x == seq) break;
+                    if (clock64() - t0 > s.idle_cycles) { quit = true; break; }
+                }
+                uint32_t* c = s.d_go + 4;
+                if (quit) { c[0] = seq; c[1] = 0; c[2] = 0; c[3] = SERVE_EXIT | 1u; }
+                else {
+                    unsigned long long p0, p1, p2;
+                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(p0), "=l"(p1) : "l"(&s.h_cmd->claims) : "memory");
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(p2) : "l"(&s.h_cmd->out) : "memory");
+                    c[0] = h.x; c[1] = h.y; c[2] = h.z; c[3] = h.w;
+                    c[4] = (uint32_t)p0; c[5] = (uint32_t)(p0 >> 32); c[6] = (uint32_t)p1; c[7] = (uint32_t)(p1 >> 32);
+                    c[8] = (uint32_t)p2; c[9] = (uint32_t)(p2 >> 32);
+                }
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(s.d_go), "r"(seq) : "memory");
+            }
+            uint32_t v;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(s.d_go) : "memory"); } while (v != seq);
+            #pragma unroll
+            for (int k = 0; k < 10; ++k) cmd_s[k] = __ldcg(s.d_go + 4 + k);
+        }
+        __syncthreads();
+        const uint32_t n_claim = cmd_s[1], n_out = cmd_s[2], flags = cmd_s[3];
+        if (flags & SERVE_EXIT) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { s.h_stat[2] = flags & 1u; s.h_stat[1] = 2u; __threadfence_system(); }
+            return;
+        }
+        const PackArgs& a = s.base;
+        Batch b;
+        b.n_claim = n_claim; b.n_out = n_out; b.serve = 1u;
+        b.inv_src = (flags & DRA_F_FRESH_INVENTORY) ? s.inv_pristine : const_cast<const uint4*>(s.base.inv_dst);
+        b.h_claims = reinterpret_cast<const uint4*>(((unsigned long long)cmd_s[5] << 32) | cmd_s[4]);
+        b.h_out_off = reinterpret_cast<const uint32_t*>(((unsigned long long)cmd_s[7] << 32) | cmd_s[6]);
+        b.h_out = reinterpret_cast<uint2*>(((unsigned long long)cmd_s[9] << 32) | cmd_s[8]);
+        b.out_off = b.h_out_off ? a.dio.d_out_off : nullptr;
+        b.have_off = b.h_out_off != nullptr;
+        if (n_claim <= s.cap_claims) fused_body<NW, true, 1>(a, b, dyn_smem, again);
+        else if (blockIdx.x == 0 && threadIdx.x == 0) a.err.set(ERR_SHARD_PLAN);          // (the host never sends such a batch)
+        // completion: every CTA's stores to the host's buffers are fenced, then the grid meets, then ONE word tells the host
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();
+        grid_barrier(a.dio.gbar, gridDim.x, a.err);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(s.h_stat), "r"(seq) : "memory");
+            __threadfence_system();
+        }
+        ++seq; again = true;
+    }
 }
 
 // ====================================================================================================

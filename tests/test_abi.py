@@ -85,7 +85,7 @@ def test_flag_constants_match_header(pkg):
     defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(DRA_(?:CFG|F)_[A-Z_]+)\s+(0x[0-9a-fA-F]+)u", text)}
     A = pkg.api
     assert defs == {"DRA_CFG_USE_GRAPH": A.CFG_USE_GRAPH, "DRA_CFG_NO_FUSED": A.CFG_NO_FUSED,
-                    "DRA_CFG_NO_DIRECT": A.CFG_NO_DIRECT, "DRA_F_NODE_SORTED": A.F_NODE_SORTED,
+                    "DRA_CFG_NO_DIRECT": A.CFG_NO_DIRECT, "DRA_CFG_RESIDENT": A.CFG_RESIDENT, "DRA_F_NODE_SORTED": A.F_NODE_SORTED,
                     "DRA_F_FRESH_INVENTORY": A.F_FRESH_INVENTORY, "DRA_F_EXHAUSTIVE": A.F_EXHAUSTIVE}
     errs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(DRA_E_[A-Z]+)\s+\((-\d+)\)", text)}
     assert errs == {"DRA_E_INVAL": A.E_INVAL, "DRA_E_CUDA": A.E_CUDA, "DRA_E_NCCL": A.E_NCCL, "DRA_E_NOMEM": A.E_NOMEM,
@@ -110,7 +110,7 @@ def test_packer_context_stays_in_registers(pkg):
         m = re.search(r"STACK:(\d+)", line)
         if m and name:
             stacks[name] = int(m.group(1))
-    hot = {k: v for k, v in stacks.items() if "k_fused" in k or "k_pack" in k}
+    hot = {k: v for k, v in stacks.items() if "k_fused" in k or "k_pack" in k or "k_serve" in k}
     assert len(hot) >= 4, stacks
     assert all(v <= 96 for v in hot.values()), hot
     # pod mode (spec §12) hands a COPY of the lane state to its out-of-line evaluator: 24 bytes, off the hot paths
