@@ -281,7 +281,7 @@ def run_ours(args):
         ctx.set_inventory(wl.gpus, wl.node_off)
         if world > 1:
             ranges = pkg.shard.plan(wl.claims["node"], wl.n_node, world)      # one-time set-up, like the inventory
-            ctx.set_shard(ranges[rank][0], ranges[rank][1], take_stray=(rank == 0))
+            ctx.set_shard_map([r[0] for r in ranges] + [ranges[-1][1]], stray_rank=0)
             hs = [None] * world
             dist.all_gather_object(hs, ctx.shard_export(wl.n_out))
             ctx.peer_import(hs)
@@ -322,6 +322,8 @@ def run_ours(args):
     stage = {}
     reps = min(50, max(10, args.steps))
     for _ in range(reps):
+        if world > 1:
+            dist.barrier()                         # (the gather waits for its peers: without this a rank's host-side delay would be timed)
         flush.fill_(1); step_dev(); ctx.sync()
         for k, v in ctx.timings_us().items():
             stage.setdefault(k, []).append(v)

@@ -60,7 +60,12 @@ const (
 	GpuFullAllocated = 0x02
 	GpuUnavailable   = 0x04
 
-	StOK = 0
+	StOK          = 0
+	StPod         = 6 // pod mode: the pod does not fit on the node
+	StSearchLimit = 7
+
+	FlagExhaustive = 0x4 // DRA_F_EXHAUSTIVE: backtracking placement search (spec §12)
+	CfgResident    = 0x8 // DRA_CFG_RESIDENT: resident kernel + doorbell for small batches
 )
 
 // Context owns one dra_ctx (one CUDA device, one stream, one inventory).  Calls are serialised, as the
@@ -72,8 +77,8 @@ type Context struct {
 
 func lastError(h *C.dra_ctx) error { return errors.New(C.GoString(C.dra_last_error(h))) }
 
-func NewContext(device int) (*Context, error) {
-	cfg := C.dra_cfg{abi_version: C.DRA_ABI_VERSION, device: C.int32_t(device)}
+func NewContext(device int, cfgFlags uint32) (*Context, error) {
+	cfg := C.dra_cfg{abi_version: C.DRA_ABI_VERSION, device: C.int32_t(device), flags: C.uint32_t(cfgFlags)}
 	var h *C.dra_ctx
 	if rc := C.dra_ctx_create(&cfg, &h); rc != 0 {
 		return nil, fmt.Errorf("dra_ctx_create: %w", lastError(nil))
@@ -146,7 +151,7 @@ func (c *Context) AllocateBatch(claims []ClaimRec, outOff []uint32, nOut int) ([
 
 // UnsuitableBatch = controller.Driver.UnsuitableNodes batched over pods; bit k of the result is set when
 // the k-th (pod, candidate node) pair is suitable.
-func (c *Context) UnsuitableBatch(claims []ClaimRec, podOff, candNodes, candOff []uint32) ([]byte, error) {
+func (c *Context) UnsuitableBatch(claims []ClaimRec, podOff, candNodes, candOff []uint32, flags uint32) ([]byte, error) {
 	nPod := len(podOff) - 1
 	bits := make([]byte, (int(candOff[nPod])+7)/8+1)
 	c.mu.Lock()
@@ -161,11 +166,34 @@ func (c *Context) UnsuitableBatch(claims []ClaimRec, podOff, candNodes, candOff 
 	}
 	rc := C.dra_unsuitable_batch(c.h, cp, C.uint32_t(len(claims)),
 		(*C.uint32_t)(unsafe.Pointer(&podOff[0])), C.uint32_t(nPod), cn,
-		(*C.uint32_t)(unsafe.Pointer(&candOff[0])), (*C.uint8_t)(unsafe.Pointer(&bits[0])))
+		(*C.uint32_t)(unsafe.Pointer(&candOff[0])), (*C.uint8_t)(unsafe.Pointer(&bits[0])), C.uint32_t(flags))
 	if rc != 0 {
 		return nil, lastError(c.h)
 	}
 	return bits, nil
+}
+
+// AllocatePodsBatch = Allocate with pod boundaries (spec §12): every pod (claims podOff[p]..podOff[p+1], one node)
+// is placed atomically; with FlagExhaustive its MIG claims are placed by the backtracking search over every valid
+// placement — what the classic mig.allocate did after UnsuitableNodes had found an assignment.
+func (c *Context) AllocatePodsBatch(claims []ClaimRec, podOff, outOff []uint32, nOut int, flags uint32) ([]OutRec, error) {
+	out := make([]OutRec, nOut)
+	if len(claims) == 0 {
+		return out, nil
+	}
+	var oo *C.uint32_t
+	if outOff != nil {
+		oo = (*C.uint32_t)(unsafe.Pointer(&outOff[0]))
+	}
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	rc := C.dra_allocate_pods_batch(c.h, (*C.dra_claim_rec)(unsafe.Pointer(&claims[0])), C.uint32_t(len(claims)),
+		(*C.uint32_t)(unsafe.Pointer(&podOff[0])), C.uint32_t(len(podOff)-1),
+		oo, (*C.dra_out_rec)(unsafe.Pointer(&out[0])), C.uint32_t(nOut), C.uint32_t(flags))
+	if rc != 0 {
+		return nil, lastError(c.h)
+	}
+	return out, nil
 }
 
 func (c *Context) DeallocateBatch(claims []ClaimRec, outOff []uint32, out []OutRec) error {

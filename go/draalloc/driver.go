@@ -27,6 +27,30 @@ type Driver struct {
 	profEnum  map[string]uint8  // profile name -> NVML GI enum
 	profID    map[uint8]int     // GI enum -> NVML profile id (device names)
 	nextGroup uint32
+	// Exhaustive: evaluate every pod atomically, MIG claims by the backtracking placement search (spec §12)
+	Exhaustive bool
+}
+
+// groupAdjacent reorders a pod's claims so that members of a co-location group (same GpuClaimName) are adjacent,
+// in order of the group's first appearance: the device only co-locates CONSECUTIVE claims of a group (spec §6).
+func groupAdjacent(claims []*ClaimAllocation) []*ClaimAllocation {
+	var runs [][]*ClaimAllocation
+	runOf := map[string]int{}
+	for _, ca := range claims {
+		if ca.IsMig && ca.GpuClaimName != "" {
+			if r, ok := runOf[ca.GpuClaimName]; ok {
+				runs[r] = append(runs[r], ca)
+				continue
+			}
+			runOf[ca.GpuClaimName] = len(runs)
+		}
+		runs = append(runs, []*ClaimAllocation{ca})
+	}
+	var out []*ClaimAllocation
+	for _, r := range runs {
+		out = append(out, r...)
+	}
+	return out
 }
 
 func (d *Driver) lower(ca *ClaimAllocation, node uint32, groups map[string]uint32) (ClaimRec, bool) {
@@ -51,6 +75,10 @@ func (d *Driver) lower(ca *ClaimAllocation, node uint32, groups map[string]uint3
 	case ca.Shared:
 		r.Kind, r.MemLimitMiB = KindShared, ca.MemLimitMiB
 	default:
+		if ca.Count < 1 || ca.Count > 32 { // DRA_MAX_COUNT; the device would answer INVALID with ONE slot
+			ca.Error = fmt.Errorf("count must be in [1, 32]")
+			return r, false
+		}
 		r.Kind, r.Count = KindGpu, uint16(ca.Count)
 	}
 	return r, true
@@ -64,7 +92,7 @@ func (d *Driver) Allocate(claims []*ClaimAllocation, selectedNode string) {
 	var off []uint32
 	var owner []*ClaimAllocation
 	nOut := 0
-	for _, ca := range claims {
+	for _, ca := range groupAdjacent(claims) {
 		if !ok {
 			ca.Error = fmt.Errorf("unknown node %q", selectedNode)
 			continue
@@ -78,7 +106,13 @@ func (d *Driver) Allocate(claims []*ClaimAllocation, selectedNode string) {
 			}
 		}
 	}
-	out, err := d.ctx.AllocateBatch(recs, off, nOut)
+	var out []OutRec
+	var err error
+	if d.Exhaustive { // the pod = the claims of this call
+		out, err = d.ctx.AllocatePodsBatch(recs, []uint32{0, uint32(len(recs))}, off, nOut, FlagExhaustive)
+	} else {
+		out, err = d.ctx.AllocateBatch(recs, off, nOut)
+	}
 	for i, ca := range owner {
 		if err != nil {
 			ca.Error = err
@@ -108,7 +142,7 @@ func (d *Driver) Allocate(claims []*ClaimAllocation, selectedNode string) {
 func (d *Driver) UnsuitableNodes(claims []*ClaimAllocation, potentialNodes []string) error {
 	groups := map[string]uint32{}
 	var recs []ClaimRec
-	for _, ca := range claims {
+	for _, ca := range groupAdjacent(claims) {
 		r, ok := d.lower(ca, 0, groups)
 		if !ok {
 			for _, ca2 := range claims {
@@ -126,7 +160,11 @@ func (d *Driver) UnsuitableNodes(claims []*ClaimAllocation, potentialNodes []str
 			cand[i] = 0xFFFFFFFF
 		}
 	}
-	bits, err := d.ctx.UnsuitableBatch(recs, []uint32{0, uint32(len(recs))}, cand, []uint32{0, uint32(len(cand))})
+	var flags uint32
+	if d.Exhaustive {
+		flags = FlagExhaustive
+	}
+	bits, err := d.ctx.UnsuitableBatch(recs, []uint32{0, uint32(len(recs))}, cand, []uint32{0, uint32(len(cand))}, flags)
 	if err != nil {
 		return err
 	}

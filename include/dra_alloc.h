@@ -315,6 +315,11 @@ int  dra_peer_import_local(dra_ctx* ctx, dra_ctx* const* ctxs);
  * With world == 1 no export is needed (the table is local).  A rank's live inventory is authoritative for its own
  * node range only. */
 int  dra_set_shard(dra_ctx* ctx, uint32_t node_lo, uint32_t node_hi, int take_stray);
+/* The whole partition: rank r serves nodes [bounds[r], bounds[r+1]) (bounds has world+1 entries, bounds[world] = n_node),
+ * stray_rank answers claims naming no node.  Since every rank reads the whole claim array, it then also COUNTS what every
+ * rank will answer — receivers know how many records to expect from each peer before the first one arrives, and the gather
+ * runs without any header or completion round.  Preferred over dra_set_shard whenever world > 1. */
+int  dra_set_shard_map(dra_ctx* ctx, const uint32_t* bounds, int stray_rank);
 int  dra_shard_export(dra_ctx* ctx, uint32_t n_out_max, uint32_t cap_per_rank, void* handle64);
 int  dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims, uint32_t n_claim,
                                       const uint32_t* d_out_off, uint32_t n_out, uint32_t flags);

@@ -59,6 +59,7 @@ SYMBOLS = {
     "dra_comm_init_local": (_i32, [_vp, _i32, _i32]),
     "dra_peer_import_local": (_i32, [_vp, _vp]),
     "dra_set_shard": (_i32, [_vp, _u32, _u32, _i32]),
+    "dra_set_shard_map": (_i32, [_vp, _vp, _i32]),
     "dra_shard_export": (_i32, [_vp, _u32, _u32, _vp]),
     "dra_allocate_batch_global_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32]),
     "dra_mps_limits_batch": (_i32, [_vp, _vp, _u32, _vp, _vp]),
@@ -334,6 +335,11 @@ class Context:
 
     def set_shard(self, node_lo: int, node_hi: int, take_stray: bool = False) -> None:
         self._check(self._lib.dra_set_shard(self._h, node_lo, node_hi, 1 if take_stray else 0))
+
+    def set_shard_map(self, bounds, stray_rank: int = 0) -> None:
+        """bounds: world + 1 node indices; this rank serves [bounds[rank], bounds[rank + 1])."""
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        self._check(self._lib.dra_set_shard_map(self._h, _ptr(b), stray_rank))
 
     def shard_export(self, n_out_max: int, cap_per_rank: int = 0, want_handle: bool = True) -> bytes:
         buf = (C.c_uint8 * 64)()

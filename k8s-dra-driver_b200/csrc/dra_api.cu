@@ -151,6 +151,9 @@ struct dra_ctx {
     long long peer_spin = 4000000000ll;         // cycles a receiver waits for a packet before ERR_PEER_TIMEOUT
     // sharded global batch
     bool shard_on = false; uint32_t shard_lo = 0, shard_hi = 0, shard_stray = 0, shard_epoch = 0;
+    uint32_t shard_last_n = 0;                  // batch size of the last sharded call (the plan hint is per batch size)
+    bool shard_map_on = false; uint32_t shard_bounds[PEER_MAX + 1] = {}; uint32_t shard_stray_rank = 0;
+    uint32_t* d_rank_slots = nullptr;           // [2][PEER_MAX] OutRec slots per rank, counted by the compaction
     uint4* d_cclaims = nullptr; uint32_t* d_coff = nullptr; size_t cap_cclaims = 0;
     unsigned long long* d_sc_status = nullptr; size_t cap_sc_status = 0;
     uint32_t* d_sc_counts = nullptr;            // device: [0] claims kept, [1] slots
@@ -407,40 +410,31 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     ctx->dio_pending = DirectIO{};
     if (dio.h_claims && !(fused && stage)) return fail(ctx, DRA_E_STATE, "direct host I/O was planned for a batch that does not take the staged single-launch kernel");
     if (fused) {
-        // the gather tail has every CTA wait for its peers' packets: all CTAs of the grid must be resident at once
+        // the gather tail has every CTA wait for its peers' packets: all CTAs of the grid must be resident at once.
+        // Shared memory left over goes to the send queue (records leave for the peers while the pack still runs).
         bool tail_ok = tail != nullptr;
+        size_t launch_smem = fused_smem;
+        uint32_t q_cap = 0;
         if (tail_ok) {
-            if (ctx->tail_cap_smem != (int)fused_smem || ctx->tail_cap_stage != (int)stage) {
-                if (fused_smem > 48 * 1024) {
-                    int& set_ = stage ? ctx->fused_smem_set_stage : ctx->fused_smem_set;
-                    if (set_ < (int)fused_smem) {
-                        if (stage) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-                        else CU(cudaFuncSetAttribute(k_fused<FUSED_NW, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-                        set_ = (int)fused_smem;
-                    }
-                }
+            static const bool no_q = getenv("DRA_NO_SENDQ") != nullptr;
+            const size_t room = fused_smem + 32 <= 225 * 1024 ? (225 * 1024 - fused_smem - 32) / 16 : 0;
+            q_cap = no_q ? 0u : (uint32_t)std::min<size_t>(room, 2048);
+            launch_smem = fused_smem + 32 + (size_t)q_cap * 16;
+            if (ctx->tail_cap_smem != (int)launch_smem || ctx->tail_cap_stage != (int)stage) {
                 int nb = 0;
-                if (stage) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, true, 1>, FUSED_NW * 32, fused_smem));
-                else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, false, 1>, FUSED_NW * 32, fused_smem));
-                ctx->tail_cap_smem = (int)fused_smem; ctx->tail_cap_stage = (int)stage; ctx->tail_cap_cta = nb * ctx->n_sm;
+                if (stage) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, true, 1>, FUSED_NW * 32, launch_smem));
+                else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, false, 1>, FUSED_NW * 32, launch_smem));
+                ctx->tail_cap_smem = (int)launch_smem; ctx->tail_cap_stage = (int)stage; ctx->tail_cap_cta = nb * ctx->n_sm;
             }
             tail_ok = (int)(n_node + 1) <= ctx->tail_cap_cta;
         }
-        if (tail_ok) { a.peer = *tail; if (tail_done) *tail_done = true; }
-        // clusters of 8 CTAs + TMA multicast when the array is staged and there are enough nodes to share it
+        if (tail_ok) { a.peer = *tail; a.q_cap = q_cap; if (tail_done) *tail_done = true; }
+        else launch_smem = fused_smem;
+        // clusters of 8 CTAs + TMA multicast: measured slower (profiles/cluster_multicast_r01e.txt: 28.1 vs 18.8 us per batch),
+        // kept as an opt-in experiment (DRA_CLUSTER=1)
         constexpr int CLS = 8;
-        // Measured (profiles/cluster_multicast_r01e.txt): multicast cuts the filter phase 4.6K -> 4.0K cycles but
-        // the cluster launch + the two cluster barriers cost far more (28.1 vs 18.8 us per batch), so it stays an
-        // opt-in experiment (DRA_CLUSTER=1), not the default.
         static const bool want_cluster = getenv("DRA_CLUSTER") != nullptr;
-        const bool cluster = stage && want_cluster && n_node + 1 >= (uint32_t)CLS;
-        int& set = cluster ? ctx->fused_smem_set_cl : (stage ? ctx->fused_smem_set_stage : ctx->fused_smem_set);
-        if (fused_smem > 48 * 1024 && set < (int)fused_smem) {
-            if (cluster) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-            else if (stage) CU(cudaFuncSetAttribute(k_fused<FUSED_NW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-            else CU(cudaFuncSetAttribute(k_fused<FUSED_NW, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-            set = (int)fused_smem;
-        }
+        const bool cluster = stage && want_cluster && n_node + 1 >= (uint32_t)CLS && !tail_ok;
         a.claims = d_claims; a.out_off = d_out_off; a.n_claim = n_claim;
         if (getenv("DRA_TIMELINE")) {           // instrumentation only: per-CTA clock stamps of the last fused launch
             if (ctx->tl_cap < (size_t)(2 * n_node + 24) * 8) {
@@ -472,8 +466,8 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
             lc.attrs = at; lc.numAttrs = 1;
             CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, true, 1>, a));
         }
-        else if (stage) CU(launch_k(k_fused<FUSED_NW, true, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), fused_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
-        else CU(launch_k(k_fused<FUSED_NW, false, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), fused_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
+        else if (stage) CU(launch_k(k_fused<FUSED_NW, true, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
+        else CU(launch_k(k_fused<FUSED_NW, false, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
         ctx->launches += 1;
         prof.mark();
         cudaError_t e = cudaGetLastError();
@@ -713,7 +707,7 @@ void dra_ctx_destroy(dra_ctx* c) {
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
                    c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels, c->d_podrec, c->d_cursor, c->d_cclaims, c->d_coff,
-                   c->d_sc_status, c->d_sc_counts, c->d_gtable};
+                   c->d_sc_status, c->d_sc_counts, c->d_gtable, c->d_rank_slots};
     for (void* p : dev) if (p) cudaFree(p);
     if (c->h_err) cudaFreeHost((void*)c->h_err);
     if (c->h_sc_counts) cudaFreeHost((void*)c->h_sc_counts);
@@ -1385,8 +1379,24 @@ int dra_allocate_batch_gather_device(dra_ctx* ctx, const dra_claim_rec* d_claims
 int dra_set_shard(dra_ctx* ctx, uint32_t node_lo, uint32_t node_hi, int take_stray) {
     if (!ctx) return DRA_E_INVAL;
     if (node_lo > node_hi || node_hi > ctx->n_node) return fail(ctx, DRA_E_INVAL, "shard [%u, %u) outside the inventory's %u nodes", node_lo, node_hi, ctx->n_node);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_sc_counts) ctx->h_sc_counts[3] = 0u;           // a new partition: the old call's count is no plan hint any more
     ctx->shard_on = true; ctx->shard_lo = node_lo; ctx->shard_hi = node_hi; ctx->shard_stray = take_stray ? 1u : 0u;
+    ctx->shard_map_on = false;
     ctx->state_epoch++;
+    return DRA_OK;
+}
+
+int dra_set_shard_map(dra_ctx* ctx, const uint32_t* bounds, int stray_rank) {
+    if (!ctx || !bounds) return DRA_E_INVAL;
+    if (stray_rank < 0 || stray_rank >= ctx->world) return fail(ctx, DRA_E_INVAL, "stray_rank %d outside the world of %d", stray_rank, ctx->world);
+    if (bounds[0] != 0 || bounds[ctx->world] != ctx->n_node) return fail(ctx, DRA_E_INVAL, "shard map must span [0, %u]", ctx->n_node);
+    for (int r = 0; r < ctx->world; ++r) if (bounds[r + 1] < bounds[r]) return fail(ctx, DRA_E_INVAL, "shard map not monotone at rank %d", r);
+    int rc = dra_set_shard(ctx, bounds[ctx->rank], bounds[ctx->rank + 1], stray_rank == ctx->rank);
+    if (rc) return rc;
+    for (int r = 0; r <= ctx->world; ++r) ctx->shard_bounds[r] = bounds[r];
+    ctx->shard_stray_rank = (uint32_t)stray_rank; ctx->shard_map_on = true;
     return DRA_OK;
 }
 
@@ -1410,7 +1420,7 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     // peers, and the call fails with DRA_E_STATE ("call again": the next plan uses the new count).
     uint32_t cap = n_claim;
     FusedPlan plan = fused_plan(ctx, cap, flags, n_local_node);
-    if (ctx->h_sc_counts && ctx->h_sc_counts[3] != 0u) {
+    if (ctx->h_sc_counts && ctx->h_sc_counts[3] != 0u && ctx->shard_last_n == n_claim) {
         const uint32_t expect = ctx->h_sc_counts[0];
         const uint32_t hi = (uint32_t)std::min<uint64_t>(n_claim, (uint64_t)expect + expect / 4 + 256);
         const uint32_t lo = (uint32_t)std::min<uint64_t>(n_claim, (uint64_t)expect + expect / 32 + 64);
@@ -1429,6 +1439,7 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
         }
     }
     if (!plan.fused) cap = n_claim;                           // sort path: no layout depends on the count
+    ctx->shard_last_n = n_claim;
     int rc = ensure_batch(ctx, std::max(cap, 1u), n_out, false);
     if (rc) return rc;
     if ((size_t)n_claim + 64 > ctx->cap_cclaims) {
@@ -1453,6 +1464,8 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
         CU(cudaHostGetDevicePointer((void**)&ctx->h_sc_counts_dev, hp, 0));
     }
     if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
+    if (!ctx->d_rank_slots) { CU(cudaMalloc((void**)&ctx->d_rank_slots, 2 * PEER_MAX * 4)); CU(cudaMemsetAsync(ctx->d_rank_slots, 0, 2 * PEER_MAX * 4, ctx->stream)); }
+    const bool counted = gather && ctx->shard_map_on;          // every rank counts every rank's slots: the gather needs no header
     // result table
     uint2* table = nullptr; PktGather g; memset(&g, 0, sizeof g);
     if (gather) {
@@ -1469,7 +1482,12 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     }
     // 1. this rank's claims, compacted in input order, node indices local to the shard
     ctx->shard_epoch += 1;
+    if (counted) g.expect = ctx->d_rank_slots + (ctx->shard_epoch & 1u) * PEER_MAX;
     ShardArgs sa; memset(&sa, 0, sizeof sa);
+    if (counted) {
+        sa.world = (uint32_t)ctx->world; sa.stray_rank = ctx->shard_stray_rank; sa.rank_slots = ctx->d_rank_slots;
+        for (int r = 0; r < ctx->world; ++r) sa.rank_hi[r] = ctx->shard_bounds[r + 1];
+    }
     sa.claims = (const uint4*)d_claims; sa.n_claim = n_claim; sa.out_off = d_out_off;
     sa.node_lo = ctx->shard_lo; sa.node_hi = ctx->shard_hi; sa.n_node_global = ctx->n_node; sa.take_stray = ctx->shard_stray;
     sa.have_off = d_out_off != nullptr;

@@ -32,6 +32,7 @@ constexpr uint32_t ERR_NOT_SORTED = 2u;
 constexpr uint32_t ERR_PEER_TIMEOUT = 3u;
 constexpr uint32_t ERR_SHARD_PLAN = 4u;      // sharded call: more claims fell into this shard than the launch was laid out for
 constexpr uint32_t ERR_WORDS = 8u;
+constexpr uint32_t PEER_MAX = 16;         // ranks of one box
 
 // Error flags: `dev` (device memory) gates later kernels of the same batch, `host` (mapped pinned
 // memory) is what the host reads after the stream drains.  Idempotent plain stores, errors are rare.
@@ -146,12 +147,25 @@ struct Dead {
 // Sink for Allocate: writes OutRecs.
 struct OutSink {
     uint2* out; uint32_t n_out; Err err; uint32_t lane;
+    // multi-GPU: every record is also appended to a queue in shared memory ({gpu, meta, slot, tag}, 16 B) from which the
+    // CTA's idle warps send it to the peers WHILE the packing warp goes on (k_fused; 0 = no queue)
+    uint32_t q_addr = 0, q_cap = 0, q_cnt = 0, q_tag = 0;
     __device__ __forceinline__ bool range(uint32_t dst, uint32_t slots) const {
         if (dst > n_out || slots > n_out - dst) { if (lane == 0) err.set(ERR_OUT_RANGE); return false; }
         return true;
     }
     __device__ __forceinline__ void put(uint32_t idx, uint32_t gpu, uint32_t m) const {
         out[idx] = make_uint2(gpu, m);
+        if (q_addr) {                                       // one shared-memory atomic per group of converged lanes
+            const uint32_t act = __activemask(), ldr = (uint32_t)__ffs(act) - 1u;
+            uint32_t base = 0;
+            if (lane == ldr) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(q_cnt), "r"((uint32_t)__popc(act)) : "memory");
+            base = __shfl_sync(act, base, ldr);
+            uint32_t ltm; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(ltm));
+            const uint32_t pos = base + (uint32_t)__popc(act & ltm);
+            if (pos < q_cap)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(q_addr + (pos << 4)), "r"(gpu), "r"(m), "r"(idx), "r"(q_tag) : "memory");
+        }
     }
     __device__ __forceinline__ bool in_range(uint32_t idx) const { return idx < n_out; }
     __device__ __forceinline__ void fail(uint32_t dst, uint32_t slots, uint32_t prof, uint32_t st) {
@@ -791,6 +805,10 @@ struct ShardArgs {
     unsigned long long* status; uint32_t* ticket; uint32_t n_tiles, epoch;
     uint32_t* counts;                 // [0] claims kept, [1] their OutRec slots
     volatile uint32_t* h_counts;      // the same, mapped host memory (plan hint for the next call)
+    // every rank reads the WHOLE array, so it can count what each rank will answer: the gather then needs no header
+    uint32_t world, stray_rank;       // world == 0: not counted
+    uint32_t rank_hi[PEER_MAX];       // rank r serves nodes [rank_hi[r-1], rank_hi[r])
+    uint32_t* rank_slots;             // [2][PEER_MAX] by epoch parity: OutRec slots per rank
     Err err;
 };
 __device__ __forceinline__ unsigned long long sc_pack(uint32_t epoch, uint32_t state, uint32_t c, uint32_t s_) {
@@ -798,9 +816,10 @@ __device__ __forceinline__ unsigned long long sc_pack(uint32_t epoch, uint32_t s
 }
 __global__ void __launch_bounds__(256)
 k_shard_compact(const ShardArgs a) {
-    __shared__ uint32_t tile_s, rowc[64], rows[64], pre_c, pre_s;
+    __shared__ uint32_t tile_s, rowc[64], rows[64], pre_c, pre_s, rs_s[PEER_MAX];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ltm = lanemask_lt();
     pdl_trigger();                                           // the allocation kernel's prologue may overlap this kernel
+    if (tid < PEER_MAX) rs_s[tid] = 0;
     if (tid == 0) {
         const uint32_t t = atomicAdd(a.ticket, 1u);
         if (t == a.n_tiles - 1) *a.ticket = 0;                    // the last ticket of this launch: ready for the next
@@ -810,6 +829,7 @@ k_shard_compact(const ShardArgs a) {
     const uint32_t tile = tile_s;
     const uint32_t w0 = tile * SC_TILE + wid * 256;
     uint4 c[8]; uint32_t keepm = 0, rk[8];
+    uint32_t own_sl[8];                                      // owner rank << 16 | slots, of every claim of the tile (world > 0)
     #pragma unroll
     for (int r = 0; r < 8; ++r) { const uint32_t i = w0 + r * 32 + lane; c[r] = i < a.n_claim ? __ldg(&a.claims[i]) : make_uint4(0, 0xFFFFFFFDu, 0, 0); }
     #pragma unroll
@@ -818,14 +838,30 @@ k_shard_compact(const ShardArgs a) {
         const bool stray = node >= a.n_node_global;
         const bool keep = i < a.n_claim && (stray ? a.take_stray != 0 : (node >= a.node_lo && node < a.node_hi));
         const uint32_t kind = c[r].x & 0xFFu, count = c[r].x >> 16;
-        const uint32_t sl = !keep ? 0u : ((kind == DRA_KIND_GPU && !stray && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u);
+        const uint32_t sl_any = i >= a.n_claim ? 0u : ((kind == DRA_KIND_GPU && !stray && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u);
+        const uint32_t sl = keep ? sl_any : 0u;
+        if (a.world) {
+            uint32_t o = 0;
+            for (uint32_t q = 0; q + 1 < a.world; ++q) o += node >= a.rank_hi[q] ? 1u : 0u;
+            own_sl[r] = ((stray ? a.stray_rank : o) << 16) | sl_any;
+        }
         const uint32_t b = __ballot_sync(FULLMASK, keep);
         rk[r] = (uint32_t)__popc(b & ltm);
         keepm |= keep ? (1u << r) : 0u;
         const uint32_t ss = __reduce_add_sync(FULLMASK, sl);
         if (lane == 0) { rowc[wid * 8 + r] = (uint32_t)__popc(b); rows[wid * 8 + r] = ss; }
     }
+    if (a.world) {                                           // slots per owner rank, for every rank (warp sums -> shared -> global)
+        for (uint32_t q = 0; q < a.world; ++q) {
+            uint32_t v = 0;
+            #pragma unroll
+            for (int r = 0; r < 8; ++r) v += (own_sl[r] >> 16) == q ? (own_sl[r] & 0xFFFFu) : 0u;
+            v = __reduce_add_sync(FULLMASK, v);
+            if (lane == 0 && v) atomicAdd(&rs_s[q], v);
+        }
+    }
     __syncthreads();
+    if (a.world && tid < a.world && rs_s[tid]) atomicAdd(&a.rank_slots[(a.epoch & 1u) * PEER_MAX + tid], rs_s[tid]);
     if (wid == 0) {
         // exclusive scan of the 64 row counts (two per lane), tile totals
         const uint32_t c0 = rowc[2 * lane], c1 = rowc[2 * lane + 1], s0 = rows[2 * lane], s1 = rows[2 * lane + 1];
@@ -867,6 +903,7 @@ k_shard_compact(const ShardArgs a) {
             if (tile == a.n_tiles - 1) {
                 a.counts[0] = ec + tc; a.counts[1] = es + ts;
                 a.h_counts[0] = ec + tc; a.h_counts[1] = es + ts; a.h_counts[3] = a.epoch;
+                if (a.world) for (uint32_t q = 0; q < PEER_MAX; ++q) a.rank_slots[((a.epoch + 1u) & 1u) * PEER_MAX + q] = 0;   // the next call's counters
             }
         }
     }
@@ -899,7 +936,6 @@ k_shard_compact(const ShardArgs a) {
 // ~10 full 128-byte lines instead of 80 sector writes — the slot rides in the packet, order does not matter.
 // Receivers poll their own (local) staging memory and scatter the records into the result table.  Latency after the
 // slowest CTA of any rank: one NVLink hop (2.5 us) + one L2 probe.
-constexpr uint32_t PEER_MAX = 16;
 constexpr uint32_t PKT_CLEAN = ~(0xF0u | 0xE000u | 0xF8000000u);      // meta bits that are always zero (start <= 15, size <= 16, status <= 7)
 struct PktGather {
     uint4* stage[PEER_MAX];       // stage[p]: THIS rank's slice inside peer p's staging area (parity applied)
@@ -914,6 +950,8 @@ struct PktGather {
     uint32_t count;               // packets (OutRec slots) this rank sends, when the host knows it ...
     const uint32_t* count_dev;    // ... else it is read here
     long long spin_limit;         // clock cycles before a missing packet becomes ERR_PEER_TIMEOUT (never a hang)
+    const uint32_t* expect;       // [world] packets every rank will send, known BEFORE the kernel starts (sharded call: every
+                                  // rank reads the whole claim array and counts all ranks' slots) — then no header is waited for
 };
 
 __device__ __forceinline__ uint32_t pkt_tag(uint32_t meta, uint32_t epoch) {
@@ -938,6 +976,7 @@ __device__ __forceinline__ void pkt_send_header(const PktGather& g, uint32_t p, 
 // CTA-collective: called by every CTA of the grid once its packets are out; the last one publishes the count
 __device__ __forceinline__ void pkt_finish_send(const PktGather& g) {
     __shared__ uint32_t last_s, total_s;
+    if (g.expect) return;                              // the receivers already know the counts: no ticket, no header
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -966,8 +1005,8 @@ __device__ __forceinline__ void pkt_receive(const PktGather& g, uint32_t T, uint
     const long long t0 = clock64();
     bool dead = false;
     for (uint32_t r = 0; r < g.world && !dead; ++r) {
-        uint32_t n = 0xFFFFFFFFu;                                     // unknown until the header is in
         if (r == g.rank) continue;                                    // own records went straight into the table
+        uint32_t n = g.expect ? min(__ldcg(g.expect + r), g.cap) : 0xFFFFFFFFu;     // unknown until the header is in
         const uint4* sl = g.my_stage + (size_t)r * g.cap;
         uint32_t spins = 0;
         for (uint32_t k = T; !dead; ) {
@@ -987,7 +1026,13 @@ __device__ __forceinline__ void pkt_receive(const PktGather& g, uint32_t T, uint
                     continue;
                 }
             }
-            if ((++spins & 63u) == 0 && clock64() - t0 > g.spin_limit) dead = true;
+            if ((++spins & 63u) == 0) {
+                if (clock64() - t0 > g.spin_limit) dead = true;
+                if (g.expect && (spins & 1023u) == 0) {              // a peer that gave up says so in its header
+                    const uint4 h = pkt_load(g.my_hdr + r);
+                    if (h.w == g.epoch && h.x == 0xFFFFFFFFu && h.y == (h.x ^ g.epoch ^ 0xA5A5A5A5u)) dead = true;
+                }
+            }
         }
         if (g.n_per && !dead) for (uint32_t k = n + T; k < g.n_per; k += NT) g.table[(size_t)r * g.n_per + k] = make_uint2(0u, 0u);
     }
@@ -1012,6 +1057,7 @@ struct PackArgs {
     const uint4* claims;          // claims in input order                             (k_fused)
     const uint32_t* out_off;      // first out slot per claim or NULL                  (k_fused)
     uint32_t n_claim;             //                                                   (k_fused)
+    uint32_t q_cap;               // multi-GPU: entries of the shared-memory send queue behind the staged claims (0: none) (k_fused)
     const uint32_t* n_dev;        // if set: the real number of claims (<= n_claim, which then only sizes the layout) (k_fused)
     const uint4* inv_src;         // inventory read from here ...
     uint4* inv_dst;               // ... and written back here (may alias inv_src)
@@ -1580,6 +1626,16 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
     const uint32_t list_addr = sbase + FU_LIST + (STAGE ? (uint32_t)NW * FU_MAXPIECE * 8u : 0u);
     const uint32_t stage_addr = STAGE ? ((list_addr + (uint32_t)fused_list_bytes(b.n_claim, NW, STAGE) + 15u) & ~15u) : 0u;
     const uint32_t sbar = sbase + FU_LIST;       // STAGE: one mbarrier per 4 KiB piece of the claim array
+    // multi-GPU send queue: behind everything else of the layout; [q_cap entries of 16 B]; its counter and end marker
+    // live in the spare words of the counts area
+    const uint32_t q_base = (sbase + (uint32_t)fused_smem_bytes(b.n_claim, NW, STAGE) + 15u) & ~15u;
+    const uint32_t q_cnt_addr = sbase + FU_CNT + 104, q_done_addr = sbase + FU_CNT + 108;
+    const bool q_on = a.peer.world != 0 && a.q_cap != 0 && has_node;
+    const uint32_t q_tag = a.peer.epoch | 0x80000000u;
+    if (q_on) {                                   // clear the tags (shared memory holds garbage at launch)
+        for (uint32_t e = threadIdx.x; e < a.q_cap; e += NW * 32) sts128(q_base + (e << 4), make_uint4(0, 0, 0, 0));
+        if (threadIdx.x == 0) { sts32(q_cnt_addr, 0); sts32(q_done_addr, 0xFFFFFFFFu); }
+    }
     // round trip 1: extents (needed for the inventory copy); table copy goes out immediately
     uint32_t g0 = 0, g1 = 0;
     if (has_node) { g0 = __ldg(&a.node_off[node]); g1 = __ldg(&a.node_off[node + 1]); }
@@ -1668,14 +1724,22 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
     const uint32_t my_list = list_addr + (lo << 2);
     const uint32_t want = has_node ? node : 0xFFFFFFFEu;
     const bool stray_cta = node == a.n_node;
-    uint32_t cntw = 0;
+    uint32_t cntw = 0, slot_l = 0;                                     // slot_l: OutRec slots of this lane's matches (gather only)
+    const bool gather = a.peer.world != 0;
     auto scan = [&](const uint32_t i, const uint32_t keyv) {          // one claim per lane; warp-uniform control flow
         // CTA n_node collects the claims that name no node of the inventory (they become INVALID, spec §3)
         const bool m = has_node ? keyv == want : (stray_cta && i < hi && keyv >= a.n_node);
-        const uint32_t b = __ballot_sync(FULLMASK, m);
-        if (b) {
-            if (m) sts32(my_list + ((cntw + (uint32_t)__popc(b & ltmask)) << 2), i);
-            cntw += (uint32_t)__popc(b);
+        const uint32_t bm = __ballot_sync(FULLMASK, m);
+        if (bm) {
+            if (m) {
+                sts32(my_list + ((cntw + (uint32_t)__popc(bm & ltmask)) << 2), i);
+                if (gather) {                                          // the packet range is reserved while the pack runs
+                    const uint32_t x_ = STAGE ? lds32(stage_addr + (i << 4)) : __ldg(reinterpret_cast<const uint32_t*>(a.claims) + 4 * (size_t)i);
+                    const uint32_t kind = x_ & 0xFFu, count = x_ >> 16;
+                    slot_l += (!stray_cta && kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, b.have_off != 0)) ? count : 1u;
+                }
+            }
+            cntw += (uint32_t)__popc(bm);
         }
     };
     constexpr int U = 8;
@@ -1714,7 +1778,23 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
     }
     DRA_STAMP(3);
     if (lane == 0) sts32(sbase + FU_CNT + (wid << 2), cntw);
+    if (gather) { slot_l = __reduce_add_sync(FULLMASK, slot_l); if (lane == 0) sts32(sbase + FU_CNT + 64 + (wid << 2), slot_l); }
     __syncthreads();
+    if (gather && threadIdx.x == NW * 32 - 1) {    // one reservation per CTA, issued now: its round trip hides behind the pack
+        uint32_t tot = 0;
+        #pragma unroll
+        for (int i = 0; i < NW; ++i) tot += lds32(sbase + FU_CNT + 64 + (i << 2));
+        sts32(sbase + FU_CNT + 100, tot);
+        sts32(sbase + FU_CNT + 96, tot ? atomicAdd(&a.peer.cursor[a.peer.parity], tot) : 0u);
+    }
+    // every record of this node fits the send queue: the idle warps send while warp 0 packs
+    bool use_q = false;
+    if (q_on) {
+        uint32_t tot = 0;
+        #pragma unroll
+        for (int i = 0; i < NW; ++i) tot += lds32(sbase + FU_CNT + 64 + (i << 2));
+        use_q = tot != 0 && tot <= a.q_cap;
+    }
     if (CL > 1) cluster_arrive();                  // this CTA has received every piece; matched by the wait at the end
     DRA_STAMP(4);
 
@@ -1752,6 +1832,7 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
             fetch(0, c_cur, p_cur);
 
             x.prof_on = a.timeline != nullptr;
+            if (use_q) { x.sink.q_addr = q_base; x.sink.q_cap = a.q_cap; x.sink.q_cnt = q_cnt_addr; x.sink.q_tag = q_tag; }
             DRA_STAMP(5);
 
             const uint32_t nseg = (cnt + SEG - 1) / SEG;
@@ -1764,12 +1845,33 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
                 c_cur = c_nxt; p_cur = p_nxt;
             }
             if (lane < ng) a.inv_dst[g0 + lane] = x.L.store(rec);
+            if (use_q) {                               // the senders may leave after this many
+                __syncwarp();
+                if (lane == 0) { const uint32_t put_ = lds32(q_cnt_addr); sts32(q_done_addr, put_); if (put_ > a.q_cap) a.err.set(ERR_PEER_TIMEOUT); }
+            }
             DRA_STAMP(6);
             if (a.timeline && lane == 0) {
                 a.timeline[blockIdx.x * 8 + 7] = (cnt & 0xFFFFu) | ((unsigned long long)(x.n_live & 0xFFFFu) << 16) |
                     ((unsigned long long)(x.t_fetch & 0xFFFF) << 32) | ((unsigned long long)(x.t_pre_a & 0xFFFF) << 48);
                 a.timeline[blockIdx.x * 8 + 0] = (unsigned long long)x.t_pre | ((unsigned long long)x.t_loop << 20) | ((unsigned long long)x.t_epi << 40);
             }
+        }
+    }
+    if (use_q && wid != 0) {
+        // the senders: warps 1..NW-1.  Entry e of the queue becomes packet (base + e) of this rank's slice at every peer.
+        asm volatile("bar.sync 1, %0;" ::"n"((NW - 1) * 32) : "memory");     // the reservation (last thread) is visible
+        const uint32_t base = lds32(sbase + FU_CNT + 96);
+        const PktGather& pg = a.peer;
+        for (uint32_t e = threadIdx.x - 32; ; e += (NW - 1) * 32) {
+            uint4 v; bool have = false;
+            while (true) {
+                if (e < a.q_cap) { v = lds128(q_base + (e << 4)); if (v.w == q_tag) { have = true; break; } }
+                const uint32_t dn = lds32(q_done_addr);
+                if (dn != 0xFFFFFFFFu && e >= dn) break;
+                __nanosleep(40);
+            }
+            if (!have) break;
+            if (base + e < pg.cap) pkt_send(pg, base + e, make_uint2(v.x, v.y), pg.slot_base + v.z);
         }
     }
     if (CL > 1) cluster_wait();                    // nobody leaves while a cluster peer may still be receiving multicasts
@@ -1797,8 +1899,8 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
     __syncthreads();                                   // warp 0's OutRecs are visible to the whole CTA
     DRA_TSTAMP(1);
     const PktGather& pg = a.peer;
-    __shared__ uint32_t pk_total_s, pk_base_s, pk_next_s;
-    if (threadIdx.x == 0) { pk_total_s = 0; pk_next_s = 0; }
+    __shared__ uint32_t pk_next_s;
+    if (threadIdx.x == 0) pk_next_s = 0;
     if (blockIdx.x == 0 && threadIdx.x == 32) pg.cursor[pg.parity ^ 1u] = 0;       // the next call's cursor
     __syncthreads();
     // the claims this CTA answers for: its node's list, or (CTA n_node) the claims that name no node (one slot each)
@@ -1807,21 +1909,10 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
         return (!stray_cta && kind == DRA_KIND_GPU && !claim_invalid(kind, 0, count, b.have_off != 0)) ? count : 1u;
     };
     auto claim_at = [&](uint32_t i) -> uint4 { return STAGE ? lds128(stage_addr + (i << 4)) : __ldcg(&a.claims[i]); };
-    uint32_t mine = 0;
-    if (has_node || stray_cta) {
-        for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
-            const uint32_t i = get.index_of(m);
-            const uint32_t dst = b.out_off ? __ldcg(&b.out_off[i]) : i, sl = slots_of(claim_at(i));
-            if (!(dst > b.n_out || sl > b.n_out - dst)) mine += sl;
-        }
-    }
-    mine = __reduce_add_sync(FULLMASK, mine);
-    if (lane == 0 && mine) atomicAdd(&pk_total_s, mine);
-    __syncthreads();
-    if (threadIdx.x == 0 && pk_total_s) pk_base_s = atomicAdd(&pg.cursor[pg.parity], pk_total_s);
-    __syncthreads();
-    if (pk_total_s) {
-        const uint32_t base = pk_base_s;
+    // (the range [base, base + total) of this rank's slice was reserved right after the filter)
+    const uint32_t pk_total = lds32(sbase + FU_CNT + 100), pk_base = lds32(sbase + FU_CNT + 96);
+    if (pk_total && !use_q) {
+        const uint32_t base = pk_base;
         for (uint32_t m = threadIdx.x; m < cnt; m += NW * 32) {
             const uint32_t i = get.index_of(m);
             const uint32_t dst = b.out_off ? __ldcg(&b.out_off[i]) : i, sl = slots_of(claim_at(i));

@@ -26,7 +26,7 @@ uid = [pkg.api.Context.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(uid[0], rank, world)
 ranges = pkg.shard.plan(w.claims["node"], w.n_node, world)
-ctx.set_shard(ranges[rank][0], ranges[rank][1], take_stray=(rank == 0))
+ctx.set_shard_map([r[0] for r in ranges] + [ranges[-1][1]], stray_rank=0)
 hs = [None] * world
 dist.all_gather_object(hs, ctx.shard_export(w.n_out)); ctx.peer_import(hs)
 d_claims = torch.from_numpy(w.claims.view(np.uint8).copy()).to(dev)

@@ -114,6 +114,39 @@ int main() {
         EXPECT_EQ_S(b.Allocation[0].Device, "gpu-0-mig-9-4-4");
         EXPECT_EQ_S(c.Allocation[0].Device, "gpu-1-mig-0-0-8");
     }
+    // --- spec §12: the exhaustive placement search behind the same surface (SetExhaustive) -----------------
+    // VERDICT r01's counter-example: slice 4 of the only GPU is busy; {1g, 3g} in that order defeats in-order first-fit
+    {
+        NodeAllocationState n; n.Node = "frag";
+        AllocatableGpu g; g.Index = 0; g.MigEnabled = true; g.MemoryBytes = 40ull << 30;
+        g.MigDevices.push_back({"1g.5gb", {4, 1}});
+        n.Gpus.push_back(g);
+        d.SetNodes({n});
+        auto a = mig("x-a", "1g.5gb"), b = mig("x-b", "3g.20gb");
+        d.UnsuitableNodes({&a, &b}, {"frag"});
+        EXPECT(a.UnsuitableNodes.size() == 1);            // default mode: a false negative
+        a.UnsuitableNodes.clear(); b.UnsuitableNodes.clear();
+        d.SetExhaustive(true);
+        d.UnsuitableNodes({&a, &b}, {"frag"});
+        EXPECT(a.UnsuitableNodes.empty() && b.UnsuitableNodes.empty());
+        d.Allocate({&a, &b}, "frag");
+        EXPECT(a.Error.empty() && b.Error.empty());
+        EXPECT_EQ_S(a.Allocation[0].Device, "gpu-0-mig-19-5-1");
+        EXPECT_EQ_S(b.Allocation[0].Device, "gpu-0-mig-9-0-4");
+        // a pod that cannot fit takes nothing (atomic) and says so
+        auto c = mig("x-c", "7g.40gb"), e = mig("x-d", "1g.5gb");
+        d.Allocate({&e, &c}, "frag");
+        EXPECT_EQ_S(c.Error, "the pod's claims do not fit on the selected node together");
+        EXPECT_EQ_S(e.Error, "the pod's claims do not fit on the selected node together");
+        EXPECT(d.BusyMask("frag", 0) == (0x10 | 0x20 | 0x0F));
+        // group members separated by another claim still share a parent (made adjacent by the host layer)
+        d.SetExhaustive(false);
+        d.SetNodes({node("n0", 2, 2)});
+        auto m1 = mig("s-1", "3g.20gb", "same"), gg = gpu("s-g"), m2 = mig("s-2", "3g.20gb", "same");
+        d.Allocate({&m1, &gg, &m2}, "n0");
+        EXPECT(m1.Error.empty() && gg.Error.empty() && m2.Error.empty());
+        EXPECT(m1.Allocation[0].GpuIndex == m2.Allocation[0].GpuIndex);
+    }
     if (failures) { printf("%d FAILED\n", failures); return 1; }
     printf("driver_test: all checks passed\n");
     return 0;

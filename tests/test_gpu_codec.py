@@ -47,8 +47,9 @@ def test_resource_slice_to_results_on_the_device(pkg, ctx, oracle):
     assert out.tobytes() == ref.tobytes()
     res = inv.results(out, names, ids)
     got = [(r["pool"], r["request"], r["device"]) if r else None for r in res]
-    assert got[:3] == [("node-a", "mig-1g-5gb-0", "gpu-2-mig-19-0-1"), ("node-a", "mig-2g-10gb", "gpu-2-mig-14-2-2"),
-                       ("node-a", "mig-3g-20gb", "gpu-2-mig-9-4-4")]   # the only parent with room for all three: the empty GPU 2
+    # GPU 0 holds one 1g device on slice 0: the run still fits there (1g@1, 2g@2-3, 3g@4-7) — lowest parent wins (spec §6)
+    assert got[:3] == [("node-a", "mig-1g-5gb-0", "gpu-0-mig-19-1-1"), ("node-a", "mig-2g-10gb", "gpu-0-mig-14-2-2"),
+                       ("node-a", "mig-3g-20gb", "gpu-0-mig-9-4-4")]
     assert got[3:5] == [("node-a", "ts-gpu", "gpu-4"), ("node-a", "mps-gpu", "gpu-4")]
     # gpu-test6: A100s with an even index; index 2 is an H100 (every 3rd from 2: 2, 5), so 0, 4, 6 — the 4th request fails
     assert [g[2] if g else None for g in got[5:]] == ["gpu-0", "gpu-4", "gpu-6", None]

@@ -32,7 +32,10 @@ def test_sharded_global_batch(pkg, oracle, world, cfg_flags, seed):
     try:
         for r, c in enumerate(ctxs):
             c.set_table(w.table); c.set_inventory(w.gpus, w.node_off)
-            c.set_shard(ranges[r][0], ranges[r][1], take_stray=(r == 0))
+            if seed == 3:
+                c.set_shard(ranges[r][0], ranges[r][1], take_stray=(r == 0))      # without the map: counts travel in a header
+            else:
+                c.set_shard_map([x[0] for x in ranges] + [ranges[-1][1]], stray_rank=0)
             c.shard_export(w.n_out, 0, want_handle=False)
         for c in ctxs:
             c.peer_import_local(ctxs)
@@ -68,7 +71,7 @@ def test_sharded_global_batch_world1_and_empty_shards(pkg, oracle):
     try:
         rng = [(0, 5), (5, 12), (12, 12)]
         for r, c in enumerate(ctxs):
-            c.set_table(w.table); c.set_inventory(w.gpus, w.node_off); c.set_shard(*rng[r], take_stray=(r == 2))
+            c.set_table(w.table); c.set_inventory(w.gpus, w.node_off); c.set_shard_map([0, 5, 12, 12], stray_rank=2)
             c.shard_export(w.n_out, 0, want_handle=False)
         for c in ctxs:
             c.peer_import_local(ctxs)
