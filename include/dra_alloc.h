@@ -356,6 +356,8 @@ int  dra_set_profiling(dra_ctx* ctx, int enabled);
 /* Instrumentation (env DRA_TIMELINE=1): 8 clock stamps per CTA of the last single-launch kernel; returns the
  * number of u64 words copied to host. */
 int  dra_debug_timeline(dra_ctx* ctx, unsigned long long* host, uint32_t n);
+/* Instrumentation (env DRA_TIMELINE=1): globaltimer of the last shard compaction's first CTA in / last CTA out. */
+int  dra_debug_shard_times(dra_ctx* ctx, unsigned long long* two);
 /* Instrumentation: enqueue an empty kernel of the given shape on ctx's stream (launch-floor calibration). */
 int  dra_debug_noop(dra_ctx* ctx, uint32_t grid, uint32_t block, uint32_t smem_bytes);
 int  dra_get_timings(dra_ctx* ctx, float* us, int n);

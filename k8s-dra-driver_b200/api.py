@@ -72,6 +72,7 @@ SYMBOLS = {
     "dra_launch_count": (_u64, [_vp]),
     "dra_set_profiling": (_i32, [_vp, _i32]),
     "dra_debug_timeline": (_i32, [_vp, _vp, _u32]),
+    "dra_debug_shard_times": (_i32, [_vp, _vp]),
     "dra_debug_noop": (_i32, [_vp, _u32, _u32, _u32]),
     "dra_get_timings": (_i32, [_vp, _vp, _i32]),
 }
@@ -380,6 +381,10 @@ class Context:
         buf = np.zeros(n_cta * 8, dtype=np.uint64)
         n = self._lib.dra_debug_timeline(self._h, _ptr(buf), len(buf))
         return buf[:n].reshape(-1, 8)
+
+    def debug_shard_times(self):
+        buf = np.zeros(2, dtype=np.uint64)
+        return buf if self._lib.dra_debug_shard_times(self._h, _ptr(buf)) == 2 else None
 
     def timings_us(self) -> dict:
         buf = (C.c_float * 5)()

@@ -151,6 +151,7 @@ struct dra_ctx {
     long long peer_spin = 4000000000ll;         // cycles a receiver waits for a packet before ERR_PEER_TIMEOUT
     // sharded global batch
     bool shard_on = false; uint32_t shard_lo = 0, shard_hi = 0, shard_stray = 0, shard_epoch = 0;
+    unsigned long long* d_sc_times = nullptr;   // instrumentation (DRA_TIMELINE)
     uint32_t shard_last_n = 0;                  // batch size of the last sharded call (the plan hint is per batch size)
     bool shard_map_on = false; uint32_t shard_bounds[PEER_MAX + 1] = {}; uint32_t shard_stray_rank = 0;
     uint32_t* d_rank_slots = nullptr;           // [2][PEER_MAX] OutRec slots per rank, counted by the compaction
@@ -707,7 +708,7 @@ void dra_ctx_destroy(dra_ctx* c) {
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,
                    c->d_pair_pod, c->d_bits, c->d_err, c->d_attrs, c->d_sels, c->d_podrec, c->d_cursor, c->d_cclaims, c->d_coff,
-                   c->d_sc_status, c->d_sc_counts, c->d_gtable, c->d_rank_slots};
+                   c->d_sc_status, c->d_sc_counts, c->d_gtable, c->d_rank_slots, c->d_sc_times};
     for (void* p : dev) if (p) cudaFree(p);
     if (c->h_err) cudaFreeHost((void*)c->h_err);
     if (c->h_sc_counts) cudaFreeHost((void*)c->h_sc_counts);
@@ -1448,7 +1449,11 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
         if ((rc = grow_nc(ctx, ctx->d_coff, 0, ncap))) return rc;
         ctx->cap_cclaims = ncap;
     }
-    const uint32_t n_tiles = std::max(1u, (n_claim + SC_TILE - 1) / SC_TILE);
+    // tiles: 256 claims while that keeps them within 1024 (one round of predecessor reads), else 2048; beyond 2M claims
+    // the look-back kernel
+    const uint32_t sc_rows = n_claim <= 256u * 1024u ? 1u : 8u;
+    const bool sc_flat = n_claim <= 2048u * 1024u;
+    const uint32_t n_tiles = std::max(1u, (n_claim + 256u * sc_rows - 1) / (256u * sc_rows));
     if ((size_t)n_tiles + 8 > ctx->cap_sc_status) {
         const size_t ncap = (size_t)n_tiles * 2 + 64;
         if ((rc = grow_nc(ctx, ctx->d_sc_status, 0, ncap))) return rc;
@@ -1494,7 +1499,15 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
     sa.cclaims = ctx->d_cclaims; sa.coff = ctx->d_coff; sa.cap = (uint32_t)std::min<size_t>(ctx->cap_cclaims, 0xFFFFFFFFu);
     sa.status = ctx->d_sc_status; sa.ticket = ctx->d_ticket + 4; sa.n_tiles = n_tiles; sa.epoch = ctx->shard_epoch;
     sa.counts = ctx->d_sc_counts; sa.h_counts = ctx->h_sc_counts_dev; sa.err = err_of(ctx);
-    k_shard_compact<<<n_tiles, 256, 0, ctx->stream>>>(sa);
+    if (getenv("DRA_TIMELINE")) {                              // instrumentation: two words, read back with dra_debug_shard_times
+        if (!ctx->d_sc_times) CU(cudaMalloc((void**)&ctx->d_sc_times, 16));
+        const unsigned long long init[2] = {~0ull, 0ull};
+        CU(cudaMemcpyAsync(ctx->d_sc_times, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+        sa.timeline = ctx->d_sc_times;
+    }
+    if (!sc_flat) k_shard_compact<<<n_tiles, 256, 0, ctx->stream>>>(sa);
+    else if (sc_rows == 1) k_shard_compact_flat<1><<<n_tiles, 256, 0, ctx->stream>>>(sa);
+    else k_shard_compact_flat<8><<<n_tiles, 256, 0, ctx->stream>>>(sa);
     ctx->launches += 1;
     // 2. the usual chain on the shard's view of the inventory, results at the claims' GLOBAL slots
     AllocView view; view.node_lo = ctx->shard_lo; view.n_node = n_local_node; view.n_dev = ctx->d_sc_counts; view.have_off = d_out_off != nullptr;
@@ -1611,6 +1624,14 @@ int dra_debug_noop(dra_ctx* ctx, uint32_t grid, uint32_t block, uint32_t smem) {
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_noop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_noop<<<grid, block, smem, ctx->stream>>>(0);
     return DRA_OK;
+}
+
+int dra_debug_shard_times(dra_ctx* ctx, unsigned long long* two) {
+    if (!ctx || !two || !ctx->d_sc_times) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(two, ctx->d_sc_times, 16, cudaMemcpyDeviceToHost);
+    return 2;
 }
 
 int dra_debug_timeline(dra_ctx* ctx, unsigned long long* host, uint32_t n) {

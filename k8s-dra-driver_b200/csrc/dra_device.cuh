@@ -797,6 +797,7 @@ k_sorted_prep(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_nod
 // look-back over the earlier tiles' status words (state | epoch | claims | slots in ONE 64-bit word, so no fence).
 // Kept claims are rewritten with the node index LOCAL to the shard; claims naming no node go to the rank with
 // take_stray set (they come back INVALID, spec §3).  coff[j] = first GLOBAL OutRec slot of kept claim j.
+__device__ __forceinline__ unsigned long long globaltimer_ns();
 constexpr uint32_t SC_TILE = 2048;
 struct ShardArgs {
     const uint4* claims; uint32_t n_claim; const uint32_t* out_off;
@@ -809,6 +810,7 @@ struct ShardArgs {
     uint32_t world, stray_rank;       // world == 0: not counted
     uint32_t rank_hi[PEER_MAX];       // rank r serves nodes [rank_hi[r-1], rank_hi[r])
     uint32_t* rank_slots;             // [2][PEER_MAX] by epoch parity: OutRec slots per rank
+    unsigned long long* timeline;     // instrumentation: [0] first CTA in, [1] last CTA out (globaltimer), or NULL
     Err err;
 };
 __device__ __forceinline__ unsigned long long sc_pack(uint32_t epoch, uint32_t state, uint32_t c, uint32_t s_) {
@@ -819,6 +821,7 @@ k_shard_compact(const ShardArgs a) {
     __shared__ uint32_t tile_s, rowc[64], rows[64], pre_c, pre_s, rs_s[PEER_MAX];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ltm = lanemask_lt();
     pdl_trigger();                                           // the allocation kernel's prologue may overlap this kernel
+    if (a.timeline && tid == 0) atomicMin(a.timeline, globaltimer_ns());
     if (tid < PEER_MAX) rs_s[tid] = 0;
     if (tid == 0) {
         const uint32_t t = atomicAdd(a.ticket, 1u);
@@ -920,6 +923,123 @@ k_shard_compact(const ShardArgs a) {
         a.cclaims[pos] = v;
         a.coff[pos] = a.out_off ? __ldg(&a.out_off[i]) : i;
     }
+    if (a.timeline) { __syncthreads(); if (tid == 0) atomicMax(a.timeline + 1, globaltimer_ns()); }
+}
+
+// The same compaction for batches of up to 2M claims, built for LATENCY (profiles/tail_timeline_r02.txt: the look-back
+// form above took 6.6 us on 20k claims — at N = 2 more than a third of what it feeds).  Small tiles (ROWS x 256
+// claims, all CTAs resident), and no chain at all: a tile publishes its aggregate and then reads the aggregates of
+// ALL its predecessors at once (8 loads per lane in flight: 256 predecessors per L2 round trip), spinning only until the last of
+// them has published.
+template <int ROWS>
+__global__ void __launch_bounds__(256, 4)             // <= 64 registers: >= 592 CTAs resident, every tile of a <= 2M-claim batch
+k_shard_compact_flat(const ShardArgs a) {
+    __shared__ uint32_t rowc[8 * ROWS], rows[8 * ROWS], pre_c, rs_s[PEER_MAX];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ltm = lanemask_lt();
+    pdl_trigger();
+    if (a.timeline && tid == 0) atomicMin(a.timeline, globaltimer_ns());
+    if (tid < PEER_MAX) rs_s[tid] = 0;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t w0 = tile * (256 * ROWS) + wid * (32 * ROWS);
+    uint4 c[ROWS]; uint32_t keepm = 0, rk[ROWS], own_sl[ROWS];
+    #pragma unroll
+    for (int r = 0; r < ROWS; ++r) { const uint32_t i = w0 + r * 32 + lane; c[r] = i < a.n_claim ? __ldg(&a.claims[i]) : make_uint4(0, 0xFFFFFFFDu, 0, 0); }
+    __syncthreads();                                         // rs_s cleared
+    #pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t i = w0 + r * 32 + lane, node = c[r].y;
+        const bool stray = node >= a.n_node_global;
+        const bool keep = i < a.n_claim && (stray ? a.take_stray != 0 : (node >= a.node_lo && node < a.node_hi));
+        const uint32_t kind = c[r].x & 0xFFu, count = c[r].x >> 16;
+        const uint32_t sl_any = i >= a.n_claim ? 0u : ((kind == DRA_KIND_GPU && !stray && !claim_invalid(kind, 0, count, a.have_off != 0)) ? count : 1u);
+        uint32_t o = 0;
+        for (uint32_t q = 0; q + 1 < a.world; ++q) o += node >= a.rank_hi[q] ? 1u : 0u;
+        own_sl[r] = ((stray ? a.stray_rank : o) << 16) | sl_any;
+        const uint32_t bm = __ballot_sync(FULLMASK, keep);
+        rk[r] = (uint32_t)__popc(bm & ltm);
+        keepm |= keep ? (1u << r) : 0u;
+        const uint32_t ss = __reduce_add_sync(FULLMASK, keep ? sl_any : 0u);
+        if (lane == 0) { rowc[wid * ROWS + r] = (uint32_t)__popc(bm); rows[wid * ROWS + r] = ss; }
+    }
+    for (uint32_t q = 0; q < a.world; ++q) {                  // slots per owner rank (for every rank: the gather's expected counts)
+        uint32_t v = 0;
+        #pragma unroll
+        for (int r = 0; r < ROWS; ++r) v += (own_sl[r] >> 16) == q ? (own_sl[r] & 0xFFFFu) : 0u;
+        v = __reduce_add_sync(FULLMASK, v);
+        if (lane == 0 && v) atomicAdd(&rs_s[q], v);
+    }
+    __syncthreads();
+    if (a.world && tid < a.world && rs_s[tid]) atomicAdd(&a.rank_slots[(a.epoch & 1u) * PEER_MAX + tid], rs_s[tid]);
+    if (wid == 0) {
+        // exclusive scan of the 8*ROWS row counts inside the tile (lane l holds rows l, l+32, ...)
+        uint32_t tc = 0, ts = 0;
+        constexpr int PER = (8 * ROWS + 31) / 32;
+        uint32_t mc[PER], run = 0;
+        #pragma unroll
+        for (int k = 0; k < PER; ++k) { const uint32_t idx = lane * PER + k; mc[k] = idx < 8u * ROWS ? rowc[idx] : 0u; run += mc[k]; ts += idx < 8u * ROWS ? rows[idx] : 0u; }
+        uint32_t x = run;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, x, d); if (lane >= (uint32_t)d) x += y; }
+        tc = __shfl_sync(FULLMASK, x, 31);
+        ts = __reduce_add_sync(FULLMASK, ts);
+        uint32_t ex = x - run;
+        #pragma unroll
+        for (int k = 0; k < PER; ++k) { const uint32_t idx = lane * PER + k; if (idx < 8u * ROWS) rowc[idx] = ex; ex += mc[k]; }
+        // publish, then the prefix = sum of ALL predecessors' aggregates (every load in flight at once)
+        unsigned long long* st = a.status;
+        if (lane == 0) atomicExch(&st[tile], sc_pack(a.epoch, 1u, tc, ts));
+        uint32_t ec = 0, es = 0;
+        const long long t0 = clock64();
+        bool dead = false;
+        for (uint32_t base = 0; base < tile && !dead; base += 256) {
+            unsigned long long v[8];
+            bool ready;
+            do {
+                ready = true;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t idx = base + k * 32 + lane;
+                    v[k] = 0;
+                    if (idx < tile) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(st + idx) : "memory");
+                }
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t idx = base + k * 32 + lane;
+                    if (idx < tile && !(((v[k] >> 52) & 0x3FFu) == (a.epoch & 0x3FFu) && (v[k] >> 62) != 0)) ready = false;
+                }
+                if (clock64() - t0 > 2000000000ll) dead = true;
+            } while (!__all_sync(FULLMASK, ready || dead));
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t idx = base + k * 32 + lane;
+                if (idx < tile) { ec += (uint32_t)((v[k] >> 26) & 0x3FFFFFFu); es += (uint32_t)(v[k] & 0x3FFFFFFu); }
+            }
+        }
+        ec = __reduce_add_sync(FULLMASK, ec); es = __reduce_add_sync(FULLMASK, es);
+        if (dead && lane == 0) a.err.set(ERR_PEER_TIMEOUT);
+        if (lane == 0) {
+            pre_c = ec;
+            if (tile == a.n_tiles - 1) {
+                a.counts[0] = ec + tc; a.counts[1] = es + ts;
+                a.h_counts[0] = ec + tc; a.h_counts[1] = es + ts; a.h_counts[3] = a.epoch;
+                if (a.world) for (uint32_t q = 0; q < PEER_MAX; ++q) a.rank_slots[((a.epoch + 1u) & 1u) * PEER_MAX + q] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t base = pre_c;
+    #pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (!((keepm >> r) & 1u)) continue;
+        const uint32_t i = w0 + r * 32 + lane;
+        const uint32_t pos = base + rowc[wid * ROWS + r] + rk[r];
+        if (pos >= a.cap) { a.err.set(ERR_OUT_RANGE); continue; }
+        uint4 v = c[r];
+        v.y = v.y >= a.n_node_global ? 0xFFFFFFFFu : v.y - a.node_lo;
+        a.cclaims[pos] = v;
+        a.coff[pos] = a.out_off ? __ldg(&a.out_off[i]) : i;
+    }
+    if (a.timeline) { __syncthreads(); if (tid == 0) atomicMax(a.timeline + 1, globaltimer_ns()); }
 }
 
 // ====================================================================================================

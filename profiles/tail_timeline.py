@@ -46,14 +46,16 @@ for it in range(40):
     tl = ctx.debug_timeline(2 * n_local + 6)
     t = tl[n_local + 4: n_local + 4 + n_local + 1].astype(np.int64)       # tail stamps: [entry, pack done, sent, ticket, received]
     e0 = t[:, 0].min()
-    rows.append([(t[:, 0].max() - e0) / 1e3, (t[:, 1].max() - e0) / 1e3, (t[:, 2].max() - e0) / 1e3, (t[:, 3].max() - e0) / 1e3, (t[:, 4].max() - e0) / 1e3])
-med = [statistics.median(r[k] for r in rows) for k in range(5)]
+    sc = ctx.debug_shard_times()
+    comp = (float(int(sc[1]) - int(sc[0])) / 1e3, float(int(e0) - int(sc[1])) / 1e3) if sc is not None else (0.0, 0.0)
+    rows.append([comp[0], comp[1], (t[:, 0].max() - e0) / 1e3, (t[:, 1].max() - e0) / 1e3, (t[:, 2].max() - e0) / 1e3, (t[:, 3].max() - e0) / 1e3, (t[:, 4].max() - e0) / 1e3])
+med = [statistics.median(r[k] for r in rows) for k in range(7)]
 out = [None] * world
 dist.all_gather_object(out, (rank, statistics.median(steps), med))
 if rank == 0:
     print(f"world {world}: one global batch of {w.n_claim} claims, {n_local} nodes per rank; medians over {len(rows)} steps, us")
-    print("rank  step(events)  | last CTA in  pack done  packets sent  ticket/header  all records in   (from the first CTA's entry, globaltimer)")
+    print("rank  step(events)  | compaction  gap to k_fused | last CTA in  pack done  packets sent  ticket/header  all records in   (from k_fused's first CTA, globaltimer)")
     for r, st, m in sorted(out):
-        print(f"{r:4d}  {st:11.2f}   | {m[0]:10.2f} {m[1]:10.2f} {m[2]:13.2f} {m[3]:14.2f} {m[4]:15.2f}")
+        print(f"{r:4d}  {st:11.2f}   | {m[0]:10.2f} {m[1]:14.2f} | {m[2]:10.2f} {m[3]:10.2f} {m[4]:13.2f} {m[5]:14.2f} {m[6]:15.2f}")
 ctx.close()
 dist.destroy_process_group()
