@@ -1121,6 +1121,55 @@ __device__ __forceinline__ void pkt_send(const PktGather& g, uint32_t pos, uint2
 // Receive side, thread T of NT: poll the local staging slices until every peer's packets are in, scatter into the table.
 // A position is done when its packet is valid, or when the peer's header says nothing will come there.
 __device__ __forceinline__ void pkt_receive(const PktGather& g, uint32_t T, uint32_t NT, const Err& err) {
+    if (g.expect) {
+        // Counts known up front: the packets of ALL peers form one work list; a thread's items are loaded together (one L2
+        // round trip for all of them, whichever peer they come from) and only the ones not yet in are asked for again.
+        // (Walking peer after peer cost one dependent round trip per peer even when everything had already arrived:
+        // profiles/tail_timeline_r02.txt, N = 8.)
+        const uint32_t want_tag = pkt_tag(0u, g.epoch);
+        const long long t0 = clock64();
+        uint32_t total = 0;
+        for (uint32_t r = 0; r < g.world; ++r) if (r != g.rank) total += min(__ldcg(g.expect + r), g.cap);
+        auto locate = [&](uint32_t j) -> const uint4* {               // item j of the concatenated slices
+            for (uint32_t r = 0; r < g.world; ++r) {
+                if (r == g.rank) continue;
+                const uint32_t n = min(__ldcg(g.expect + r), g.cap);
+                if (j < n) return g.my_stage + (size_t)r * g.cap + j;
+                j -= n;
+            }
+            return g.my_stage;
+        };
+        constexpr int MAXI = 4;
+        bool dead = false;
+        for (uint32_t b0 = T; b0 < total && !dead; b0 += NT * MAXI) {
+            const uint4* p[MAXI]; uint32_t pend = 0;
+            #pragma unroll
+            for (int i = 0; i < MAXI; ++i) { const uint32_t j = b0 + (uint32_t)i * NT; p[i] = locate(j < total ? j : 0u); if (j < total) pend |= 1u << i; }
+            uint32_t spins = 0;
+            while (pend && !dead) {
+                uint4 v[MAXI];
+                #pragma unroll
+                for (int i = 0; i < MAXI; ++i) if ((pend >> i) & 1u) v[i] = pkt_load(p[i]);
+                #pragma unroll
+                for (int i = 0; i < MAXI; ++i)
+                    if (((pend >> i) & 1u) && v[i].w == g.epoch && (v[i].y & ~PKT_CLEAN) == want_tag) {
+                        g.table[v[i].z] = make_uint2(v[i].x, v[i].y & PKT_CLEAN);
+                        pend &= ~(1u << i);
+                    }
+                if (pend && (++spins & 63u) == 0) {
+                    if (clock64() - t0 > g.spin_limit) dead = true;
+                    if ((spins & 1023u) == 0)                          // a peer that gave up says so in its header
+                        for (uint32_t r = 0; r < g.world; ++r) {
+                            if (r == g.rank) continue;
+                            const uint4 h = pkt_load(g.my_hdr + r);
+                            if (h.w == g.epoch && h.x == 0xFFFFFFFFu && h.y == (h.x ^ g.epoch ^ 0xA5A5A5A5u)) dead = true;
+                        }
+                }
+            }
+        }
+        if (dead) err.set(ERR_PEER_TIMEOUT);
+        return;
+    }
     const uint32_t want_tag = pkt_tag(0u, g.epoch);
     const long long t0 = clock64();
     bool dead = false;
@@ -2091,28 +2140,28 @@ k_serve(const ServeArgs s) {
     bool again = false;
     if (blockIdx.x == 0 && threadIdx.x == 0) { s.h_stat[1] = 1u; __threadfence_system(); }
     for (;;) {
-        if (threadIdx.x == 0) {
-            if (blockIdx.x == 0) {
-                // the doorbell: one 16-byte load of {seq, n_claim, n_out, flags} per poll
-                const long long t0 = clock64();
-                uint4 h; bool quit = false;
-                for (;;) {
-                    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(s.h_cmd) : "memory");
-                    if (h.x == seq) break;
-                    if (clock64() - t0 > s.idle_cycles) { quit = true; break; }
-                }
-                uint32_t* c = s.d_go + 4;
-                if (quit) { c[0] = seq; c[1] = 0; c[2] = 0; c[3] = SERVE_EXIT | 1u; }
-                else {
-                    unsigned long long p0, p1, p2;
-                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(p0), "=l"(p1) : "l"(&s.h_cmd->claims) : "memory");
-                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(p2) : "l"(&s.h_cmd->out) : "memory");
-                    c[0] = h.x; c[1] = h.y; c[2] = h.z; c[3] = h.w;
-                    c[4] = (uint32_t)p0; c[5] = (uint32_t)(p0 >> 32); c[6] = (uint32_t)p1; c[7] = (uint32_t)(p1 >> 32);
-                    c[8] = (uint32_t)p2; c[9] = (uint32_t)(p2 >> 32);
-                }
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(s.d_go), "r"(seq) : "memory");
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            // the doorbell: lanes 0..3 read 16 bytes each of the 64-byte command line — ONE PCIe read per poll brings the
+            // sequence number AND the whole command (the host writes the fields first, the sequence number last)
+            const long long t0 = clock64();
+            uint4 h = make_uint4(0, 0, 0, 0); bool quit = false;
+            for (;;) {
+                if (threadIdx.x < 4)
+                    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w)
+                                 : "l"((const uint4*)(const void*)const_cast<const ServeCmd*>(s.h_cmd) + threadIdx.x) : "memory");
+                const uint32_t got = __shfl_sync(FULLMASK, h.x, 0);
+                if (got == seq) break;
+                if (clock64() - t0 > s.idle_cycles) { quit = true; break; }
             }
+            uint32_t* c = s.d_go + 4;
+            if (threadIdx.x < 4) {
+                if (quit) { if (threadIdx.x == 0) { c[0] = seq; c[1] = 0; c[2] = 0; c[3] = SERVE_EXIT | 1u; } }
+                else *reinterpret_cast<uint4*>(c + 4 * threadIdx.x) = h;      // {seq,n,n_out,flags} {claims,out_off} {out,-}
+            }
+            __syncwarp();
+            if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(s.d_go), "r"(seq) : "memory"); }
+        }
+        if (threadIdx.x == 0) {
             uint32_t v;
             do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(s.d_go) : "memory"); } while (v != seq);
             #pragma unroll
@@ -2135,13 +2184,17 @@ k_serve(const ServeArgs s) {
         b.have_off = b.h_out_off != nullptr;
         if (n_claim <= s.cap_claims) fused_body<NW, true, 1>(a, b, dyn_smem, again);
         else if (blockIdx.x == 0 && threadIdx.x == 0) a.err.set(ERR_SHARD_PLAN);          // (the host never sends such a batch)
-        // completion: every CTA's stores to the host's buffers are fenced, then the grid meets, then ONE word tells the host
+        // completion: every CTA fences its stores to the host's buffers and takes a ticket; the last one tells the host
+        // (one word).  Nobody waits here: the next doorbell cannot ring before the host has seen this word.
         __syncthreads();
-        if (threadIdx.x == 0) __threadfence_system();
-        grid_barrier(a.dio.gbar, gridDim.x, a.err);
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(s.h_stat), "r"(seq) : "memory");
+        if (threadIdx.x == 0) {
             __threadfence_system();
+            if (atomicAdd(s.d_go + 2, 1u) == gridDim.x - 1) {
+                s.d_go[2] = 0;
+                __threadfence();
+                asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(s.h_stat), "r"(seq) : "memory");
+                __threadfence_system();
+            }
         }
         ++seq; again = true;
     }
