@@ -358,6 +358,9 @@ int  dra_set_profiling(dra_ctx* ctx, int enabled);
 int  dra_debug_timeline(dra_ctx* ctx, unsigned long long* host, uint32_t n);
 /* Instrumentation (env DRA_TIMELINE=1): globaltimer of the last shard compaction's first CTA in / last CTA out. */
 int  dra_debug_shard_times(dra_ctx* ctx, unsigned long long* two);
+/* Instrumentation: globaltimer stamps of the resident kernel's last batch — doorbell seen, CTA 0's egress issued, every CTA
+ * fenced, completion word written.  Stops the resident kernel. */
+int  dra_debug_serve_times(dra_ctx* ctx, unsigned long long* four);
 /* Instrumentation: enqueue an empty kernel of the given shape on ctx's stream (launch-floor calibration). */
 int  dra_debug_noop(dra_ctx* ctx, uint32_t grid, uint32_t block, uint32_t smem_bytes);
 int  dra_get_timings(dra_ctx* ctx, float* us, int n);

@@ -73,6 +73,7 @@ SYMBOLS = {
     "dra_set_profiling": (_i32, [_vp, _i32]),
     "dra_debug_timeline": (_i32, [_vp, _vp, _u32]),
     "dra_debug_shard_times": (_i32, [_vp, _vp]),
+    "dra_debug_serve_times": (_i32, [_vp, _vp]),
     "dra_debug_noop": (_i32, [_vp, _u32, _u32, _u32]),
     "dra_get_timings": (_i32, [_vp, _vp, _i32]),
 }
@@ -381,6 +382,10 @@ class Context:
         buf = np.zeros(n_cta * 8, dtype=np.uint64)
         n = self._lib.dra_debug_timeline(self._h, _ptr(buf), len(buf))
         return buf[:n].reshape(-1, 8)
+
+    def debug_serve_times(self):
+        buf = np.zeros(4, dtype=np.uint64)
+        return buf if self._lib.dra_debug_serve_times(self._h, _ptr(buf)) == 4 else None
 
     def debug_shard_times(self):
         buf = np.zeros(2, dtype=np.uint64)

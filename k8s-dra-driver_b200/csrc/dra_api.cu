@@ -1626,6 +1626,14 @@ int dra_debug_noop(dra_ctx* ctx, uint32_t grid, uint32_t block, uint32_t smem) {
     return DRA_OK;
 }
 
+int dra_debug_serve_times(dra_ctx* ctx, unsigned long long* four) {
+    if (!ctx || !four || !ctx->d_go) return 0;
+    cudaSetDevice(ctx->device);
+    if (serve_stop(ctx)) return 0;
+    cudaMemcpy(four, ctx->d_go + 32, 32, cudaMemcpyDeviceToHost);
+    return 4;
+}
+
 int dra_debug_shard_times(dra_ctx* ctx, unsigned long long* two) {
     if (!ctx || !two || !ctx->d_sc_times) return 0;
     cudaSetDevice(ctx->device);

@@ -2153,6 +2153,7 @@ k_serve(const ServeArgs s) {
                 if (got == seq) break;
                 if (clock64() - t0 > s.idle_cycles) { quit = true; break; }
             }
+            if (threadIdx.x == 0) reinterpret_cast<unsigned long long*>(s.d_go + 32)[0] = globaltimer_ns();    // instrumentation: doorbell seen
             uint32_t* c = s.d_go + 4;
             if (threadIdx.x < 4) {
                 if (quit) { if (threadIdx.x == 0) { c[0] = seq; c[1] = 0; c[2] = 0; c[3] = SERVE_EXIT | 1u; } }
@@ -2188,12 +2189,15 @@ k_serve(const ServeArgs s) {
         // (one word).  Nobody waits here: the next doorbell cannot ring before the host has seen this word.
         __syncthreads();
         if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) reinterpret_cast<unsigned long long*>(s.d_go + 32)[1] = globaltimer_ns();        // CTA 0's egress stores issued
             __threadfence_system();
             if (atomicAdd(s.d_go + 2, 1u) == gridDim.x - 1) {
                 s.d_go[2] = 0;
                 __threadfence();
+                reinterpret_cast<unsigned long long*>(s.d_go + 32)[2] = globaltimer_ns();                           // every CTA fenced
                 asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(s.h_stat), "r"(seq) : "memory");
                 __threadfence_system();
+                reinterpret_cast<unsigned long long*>(s.d_go + 32)[3] = globaltimer_ns();                           // completion word out
             }
         }
         ++seq; again = true;
