@@ -83,3 +83,67 @@ def test_plan_is_balanced_and_contiguous(pkg):
         loads = [int(((w.claims["node"] >= a) & (w.claims["node"] < b)).sum()) for a, b in r]
         assert sum(loads) == w.n_claim
         assert max(loads) - min(loads) <= 2 * (w.n_claim // w.n_node + 50)
+
+
+# ---- the GLOBAL batch form (round 2): every rank holds the whole inventory and the whole claim array -------------------
+def _global_worker(rank, world, port, q):
+    """What dra_allocate_batch_global_device does, restated with the CPU oracle standing in for the GPU: keep the claims of
+    this rank's node range IN INPUT ORDER (stable compaction), allocate them on the global inventory, and all-gather the
+    records as (global slot, OutRec) packets; every rank assembles the table from its own records + the packets."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    pkg = importlib.import_module("k8s-dra-driver_b200")
+    from oracle import oracle as O
+    R = pkg.records
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = pkg.synth.mixed(3000, 31, 6)
+        ranges = pkg.shard.plan(w.claims["node"], w.n_node, world)
+        lo, hi = ranges[rank]
+        node = w.claims["node"]
+        keep = ((node >= lo) & (node < hi)) | ((node >= w.n_node) & (rank == 0))      # stray claims: rank 0
+        idx = np.nonzero(keep)[0]
+        mine = w.claims[idx].copy()
+        slots = R.claim_slots(w.claims, w.n_node)
+        goff = w.out_off                                                            # GLOBAL first slot of every claim
+        loff = np.zeros(len(idx), np.uint32); loff[1:] = np.cumsum(slots[idx][:-1])
+        out, inv = O.allocate(w.gpus, w.node_off, w.table, mine, loff, int(slots[idx].sum()))
+        # packets: (global slot, record) for every slot this rank answers
+        gs = np.concatenate([np.arange(goff[i], goff[i] + slots[i]) for i in idx]).astype(np.int64) if len(idx) else np.zeros(0, np.int64)
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([len(gs)], dtype=torch.int64))
+        pad = int(max(int(s_.item()) for s_ in sizes))
+        buf = np.zeros((pad, 2), dtype=np.int64)
+        buf[: len(gs), 0] = gs; buf[: len(gs), 1] = out.view(np.uint64).astype(np.int64)
+        gathered = [torch.zeros(pad, 2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(buf))
+        table = np.zeros(w.n_out, dtype=np.uint64)
+        for r in range(world):
+            n = int(sizes[r].item())
+            g = gathered[r].numpy()
+            table[g[:n, 0]] = g[:n, 1].astype(np.uint64)
+        ref, ref_inv = O.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+        ok = table.tobytes() == ref.tobytes()
+        g0, g1 = int(w.node_off[lo]), int(w.node_off[hi])
+        ok = ok and inv[g0:g1].tobytes() == ref_inv[g0:g1].tobytes()               # a rank's inventory is authoritative for its range
+        q.put((rank, ok, sum(int(s_.item()) for s_ in sizes) == w.n_out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_global_batch_sharded_by_node_range(world, oracle):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_global_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok and covered for _, ok, covered in res)       # same bytes as one rank, and every slot answered exactly once
