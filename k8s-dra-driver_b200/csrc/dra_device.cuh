@@ -2153,7 +2153,7 @@ k_serve(const ServeArgs s) {
                 if (got == seq) break;
                 if (clock64() - t0 > s.idle_cycles) { quit = true; break; }
             }
-            if (threadIdx.x == 0) reinterpret_cast<unsigned long long*>(s.d_go + 32)[0] = globaltimer_ns();    // instrumentation: doorbell seen
+            if (threadIdx.x == 0 && !quit && !(h.w & SERVE_EXIT)) reinterpret_cast<unsigned long long*>(s.d_go + 32)[0] = globaltimer_ns();    // instrumentation: doorbell seen
             uint32_t* c = s.d_go + 4;
             if (threadIdx.x < 4) {
                 if (quit) { if (threadIdx.x == 0) { c[0] = seq; c[1] = 0; c[2] = 0; c[3] = SERVE_EXIT | 1u; } }

@@ -9,6 +9,9 @@ import subprocess
 import sys
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct",
+        "smsp__inst_executed_op_tma_ld.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "smsp__inst_executed_op_shared_ld.sum",
@@ -68,9 +71,12 @@ def kernel(path):
                 return float(r[hdr.index(k)].replace(",", ""))
             except (ValueError, IndexError):
                 return None
-        l2, dr, dw = val("lts__t_bytes.sum"), val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
-        if l2 and dr is not None:
-            print(f"  {'(derived) L2 bytes / DRAM bytes':<86}{l2 / max(1.0, dr + (dw or 0)):>16.1f} x")
+        def scaled(k):
+            v, u = val(k), units[hdr.index(k)] if k in hdr else ""
+            return None if v is None else v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        xb, dr, dw = scaled("l1tex__m_xbar2l1tex_read_bytes.sum"), scaled("dram__bytes_read.sum"), scaled("dram__bytes_write.sum")
+        if xb and dr is not None:
+            print(f"  {'(derived) L2 -> SM bytes / DRAM bytes (re-reads served by L2)':<86}{xb / max(1.0, dr + (dw or 0)):>16.1f} x")
 
 
 if __name__ == "__main__":
