@@ -2273,7 +2273,20 @@ __device__ __noinline__ uint32_t pod_eval(Lane& L, const uint32_t lane, const ui
         }
         if (ps.failed) status = DRA_ST_POD;
     }
-    // ---- 3. the MIG claims: depth-first search in canonical order (GPUs ascending, starts ascending) ----
+    // ---- 3. pre-check: a MIG claim with no placement at all on the node as it stands sinks the pod (one vote per claim) ----
+    if (!status) {
+        uint32_t mm = migmask;
+        while (mm && !status) {
+            const uint32_t pos = (uint32_t)__ffs(mm) - 1u; mm &= mm - 1u;
+            const uint4 c = get(pos);
+            const uint32_t e = tbl_s[L.model * DRA_MAX_PROFILES + ((c.x >> 8) & 0xFFu)];
+            bool ok = L.valid && (L.flags & BLOCKED) == DRA_GPU_MIG_ENABLED && (e >> 16) != 0;
+            if (c.z != 0) ok = sel_pass(sc, c.z, g0 + gl, L.valid) && ok;
+            const bool fits = ok && (fit_map(~L.busy & 0xFFFFu, e & 0xFFu) & (e >> 16)) != 0;
+            if (!(__ballot_sync(gmask, fits) & gmask)) status = DRA_ST_POD;
+        }
+    }
+    // ---- the MIG claims: depth-first search in canonical order (GPUs ascending, starts ascending) ----
     uint32_t chosen = 0;                       // bit pos: this lane's GPU holds the claim at position pos
     unsigned long long st_lo = 0, st_hi = 0;   // its start there, one nibble per position
     if (!status && migmask) {

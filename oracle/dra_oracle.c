@@ -629,6 +629,16 @@ static int pod_eval(dra_gpu_rec* gpus, uint32_t g0, uint32_t ng, const dra_profi
         ok = j.all_ok;
     }
     pod_search ps; memset(&ps, 0, sizeof ps);
+    for (uint32_t i = 0; ok && i < k; i++) {             /* step 3 pre-check: a claim with no placement at all in S' sinks the pod */
+        const dra_claim_rec* c = &claims[mig[i]];
+        int any = 0;
+        for (uint32_t g = 0; g < ng && !any; g++) {
+            dra_prof_ent e = tbl[work[g].model].ent[c->profile];
+            if (!gpu_offers(&work[g], e) || (work[g].flags & DRA_GPU_FULL_ALLOCATED) || !sel_pass(claim_sel(c), g0 + g)) continue;
+            any = lowest_fit(work[g].busy, e) >= 0;
+        }
+        if (!any) ok = 0;
+    }
     if (ok && k) {                                       /* step 3: the MIG claims, canonical DFS */
         ps.gpus = work; ps.g0 = g0; ps.ng = ng; ps.tbl = tbl; ps.claims = claims; ps.mig = mig; ps.k = k;
         ps.exhaustive = exhaustive;

@@ -217,6 +217,18 @@ def eval_pod(G, g0, g1, table, pod, n_node, exhaustive, have_off=True):
     mig = [i for i, c in enumerate(pod) if c["kind"] == 1]
     budget = [0]
     choice = {}
+    for i in mig:                                     # pre-check: no placement at all for this claim on the node as it stands
+        c = pod[i]
+        fits = False
+        for g in W:
+            size, mask = table[g["model"]][c["profile"]]
+            if not g["mig"] or g["unavail"] or g["full"] or not mask:
+                continue
+            if any((mask >> s) & 1 and not (set(range(s, s + size)) & g["used"]) for s in range(16)):
+                fits = True
+                break
+        if not fits:
+            return failed(6)
 
     def options(level):
         c = pod[mig[level]]
