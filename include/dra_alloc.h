@@ -334,6 +334,11 @@ int  dra_mps_limits_batch(dra_ctx* ctx, const int64_t* bytes, uint32_t n, int64_
 int  dra_imex_offsets_batch(dra_ctx* ctx, const int32_t* used, const uint32_t* dom_off, uint32_t n_dom,
                             int32_t step, int32_t limit, int32_t* out);
 
+/* One-time calibration (optional): measures, on this device and the loaded inventory, up to which batch size the
+ * single-launch kernel beats the bucket + pack chain, and uses that crossover from then on (the built-in values were
+ * measured on one B200 box).  The live inventory is preserved.  *crossover_claims (may be NULL) receives the result. */
+int  dra_calibrate(dra_ctx* ctx, uint32_t* crossover_claims);
+
 /* ---- resident mode (DRA_CFG_RESIDENT) ------------------------------------------------------------------------------
  * Optional explicit control: start the resident kernel now (the first eligible dra_allocate_batch would), stop it (every
  * other entry point of the context does so implicitly before it runs).  dra_serve_batches: batches it has answered. */

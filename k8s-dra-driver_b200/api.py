@@ -64,6 +64,7 @@ SYMBOLS = {
     "dra_allocate_batch_global_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32]),
     "dra_mps_limits_batch": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "dra_imex_offsets_batch": (_i32, [_vp, _vp, _vp, _u32, C.c_int32, C.c_int32, _vp]),
+    "dra_calibrate": (_i32, [_vp, C.POINTER(_u32)]),
     "dra_serve_start": (_i32, [_vp]),
     "dra_serve_stop": (_i32, [_vp]),
     "dra_serve_batches": (_u64, [_vp]),
@@ -357,6 +358,12 @@ class Context:
         blob = b"".join(handles)
         buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
         self._check(self._lib.dra_peer_import(self._h, C.cast(buf, C.c_void_p)))
+
+    def calibrate(self) -> int:
+        """Measure the single-launch / sort-path crossover on this device + inventory; returns the claim count."""
+        v = _u32(0)
+        self._check(self._lib.dra_calibrate(self._h, C.byref(v)))
+        return int(v.value)
 
     # -- resident mode ----------------------------------------------------------------------------------
     def serve_start(self) -> None:

@@ -111,6 +111,8 @@ struct dra_ctx {
     // per function, not per context — a lazily "grown" per-context value would LOWER it under another context's feet
     int hist8_smem_set = 1 << 30, hist_smem_set = 1 << 30, small_smem_set = 1 << 30, fused_smem_set = 1 << 30, fused_smem_set_stage = 1 << 30, fused_smem_set_cl = 1 << 30;
     uint64_t fused_max_work = 3000000ull;   // n_node * n_claim up to which the single-launch kernel is used
+    uint32_t fused_max_one_wave = 14000u, fused_max_multi = 7500u;   // claims up to which it beats the sort path: measured on one box
+                                                                     // (profiles/path_crossover_r01f.txt); dra_calibrate re-measures them here
     // direct host I/O of the single-launch kernel (DirectIO in dra_device.cuh)
     DirectIO dio_pending{};                 // set by dra_allocate_batch for the next launch_allocate, then cleared
     uint32_t* d_gbar = nullptr;             // grid barrier words
@@ -293,7 +295,7 @@ FusedPlan fused_plan(const dra_ctx* ctx, uint32_t n_claim, uint32_t flags, uint3
     // Measured crossover against the sort path (profiles/path_crossover_r01f.txt): the single launch costs about
     // 4 us + 1.2 us per 1000 claims while all CTAs fit one wave (10 us + 1.4 us beyond), the sort path about
     // 20 us + 0.2 us per 1000 claims.
-    const uint32_t fused_max_claims = (int)(n_node + 1) <= ctx->n_sm ? 14000u : 7500u;   // one wave of CTAs or not
+    const uint32_t fused_max_claims = (int)(n_node + 1) <= ctx->n_sm ? ctx->fused_max_one_wave : ctx->fused_max_multi;   // one wave of CTAs or not
     p.fused = !(flags & DRA_F_NODE_SORTED) && !(ctx->cfg_flags & DRA_CFG_NO_FUSED) && n_claim <= fused_max_claims &&
               (uint64_t)n_node * n_claim <= ctx->fused_max_work && p.smem <= 225 * 1024 && n_node <= 16384;
     return p;
@@ -537,6 +539,13 @@ int raise_smem_limits(dra_ctx* ctx, int optin) {
     if ((rc = raise_one(ctx, k_bucket_hist8, optin))) return rc;
     if ((rc = raise_one(ctx, k_bucket_hist, optin))) return rc;
     if ((rc = raise_one(ctx, k_serve<FUSED_NW>, optin))) return rc;
+    // The compaction runs right before the single-launch kernel, which wants the SM's L1/shared split at "all shared".  An SM
+    // cannot hold CTAs of kernels with different splits at once: with the default split the dependent kernel's CTAs could
+    // not be placed early (programmatic dependent launch) and the SMs were re-configured in between (~6 us from the
+    // compaction's last CTA to k_fused's first, profiles/tail_timeline_r02_n2.txt).  Same split for both.
+    CU(cudaFuncSetAttribute(k_shard_compact_flat<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_shard_compact_flat<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_shard_compact, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return DRA_OK;
 }
 
@@ -1581,6 +1590,65 @@ int dra_imex_offsets_batch(dra_ctx* ctx, const int32_t* used, const uint32_t* do
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_u); cudaFree(d_o); cudaFree(d_r);
     if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "dra_imex_offsets_batch: %s", cudaGetErrorString(e));
+    return DRA_OK;
+}
+
+// One-time calibration of the single-launch / sort-path crossover on THIS device and THIS inventory: synthetic MIG claims
+// (uniform over the nodes) at a few batch sizes through both chains, CUDA events, best of 5; the live inventory is
+// saved and restored.  Sets the claim count up to which dra_allocate_batch takes the single-launch kernel.
+int dra_calibrate(dra_ctx* ctx, uint32_t* crossover_claims) {
+    if (!ctx) return DRA_E_INVAL;
+    QUIESCE();
+    if (!ctx->d_inv_live || !ctx->n_node) return fail(ctx, DRA_E_STATE, "dra_set_inventory has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t sizes[] = {2000, 4000, 6000, 8000, 10000, 12000, 14000, 16000, 20000, 24000};
+    const uint32_t n_max = 24000;
+    int rc = ensure_batch(ctx, n_max, n_max, true);
+    if (rc) return rc;
+    std::vector<dra_claim_rec> h(n_max);
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    for (uint32_t i = 0; i < n_max; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        h[i].kind = DRA_KIND_MIG; h[i].profile = (uint8_t)((x >> 40) % 3); h[i].count = 1;
+        h[i].node = (uint32_t)(x % ctx->n_node); h[i].mem_limit_mib = 0; h[i].group = 0;
+    }
+    uint4* d_save = nullptr;
+    CU(cudaMalloc((void**)&d_save, (size_t)ctx->n_gpu * 16 + 16));
+    CU(cudaMemcpy(d_save, ctx->d_inv_live, (size_t)ctx->n_gpu * 16, cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(ctx->d_claims, h.data(), (size_t)n_max * 16, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const uint32_t saved_flags = ctx->cfg_flags;
+    const uint32_t saved_a = ctx->fused_max_one_wave, saved_b = ctx->fused_max_multi;
+    const bool prof = ctx->profiling; ctx->profiling = false;
+    uint32_t best = 0; bool lost = false;
+    for (uint32_t n : sizes) {
+        float t[2] = {1e30f, 1e30f};
+        for (int path = 0; path < 2 && rc == DRA_OK; ++path) {
+            ctx->cfg_flags = (saved_flags & ~DRA_CFG_NO_FUSED) | (path ? DRA_CFG_NO_FUSED : 0u);
+            ctx->fused_max_one_wave = ctx->fused_max_multi = path ? 0u : 0xFFFFFFFFu;
+            if (path == 0 && !fused_plan(ctx, n, DRA_F_FRESH_INVENTORY, ctx->n_node).fused) { t[0] = 1e30f; continue; }   // not launchable at this size
+            for (int rep = 0; rep < 6 && rc == DRA_OK; ++rep) {
+                cudaEventRecord(e0, ctx->stream);
+                rc = launch_allocate(ctx, ctx->d_claims, n, nullptr, ctx->d_out, n, DRA_F_FRESH_INVENTORY);
+                cudaEventRecord(e1, ctx->stream);
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, DRA_E_CUDA, "calibration run failed");
+                float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+                if (rep) t[path] = std::min(t[path], ms);
+            }
+        }
+        if (rc) break;
+        if (t[0] <= t[1] && !lost) best = n; else lost = true;          // the first size at which the sort path wins ends the range
+    }
+    ctx->cfg_flags = saved_flags; ctx->profiling = prof;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaMemcpy(ctx->d_inv_live, d_save, (size_t)ctx->n_gpu * 16, cudaMemcpyDeviceToDevice);
+    cudaFree(d_save);
+    (void)check_err(ctx);
+    if (rc) { ctx->fused_max_one_wave = saved_a; ctx->fused_max_multi = saved_b; return rc; }
+    if ((int)(ctx->n_node + 1) <= ctx->n_sm) { ctx->fused_max_one_wave = best; ctx->fused_max_multi = saved_b; }
+    else { ctx->fused_max_multi = best; ctx->fused_max_one_wave = saved_a; }
+    ctx->state_epoch++;
+    if (crossover_claims) *crossover_claims = best;
     return DRA_OK;
 }
 

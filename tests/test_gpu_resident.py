@@ -80,3 +80,21 @@ def test_resident_kernel_is_stopped_by_destroy(pkg, oracle):
         d.set_table(w.table); d.set_inventory(w.gpus, w.node_off)
         assert d.allocate(w.claims).tobytes() == ref.tobytes()
     pc.free(); po.free()
+
+
+def test_calibration_keeps_state_and_results(pkg, oracle):
+    """dra_calibrate measures the single-launch / sort-path crossover on this box; it must leave the inventory alone and
+    the answers unchanged on both sides of whatever crossover it finds."""
+    w = pkg.synth.cfg2(9000, 60)
+    first, inv1 = oracle.allocate(w.gpus, w.node_off, w.table, w.claims[:3000])
+    with pkg.api.Context(device=0) as c:
+        c.set_table(w.table); c.set_inventory(w.gpus, w.node_off)
+        assert c.allocate(w.claims[:3000].copy()).tobytes() == first.tobytes()
+        x = c.calibrate()
+        print("single-launch kernel beats the sort path up to", x, "claims on this box (60 nodes)")
+        assert 0 <= x <= 24000
+        assert c.get_inventory().tobytes() == inv1.tobytes()
+        for n in (500, 5000, 9000):
+            ref, _ = oracle.allocate(inv1, w.node_off, w.table, w.claims[:n])
+            c.set_inventory(inv1, w.node_off)
+            assert c.allocate(w.claims[:n].copy()).tobytes() == ref.tobytes()
