@@ -444,8 +444,8 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
                 if (ctx->d_timeline) CU(cudaFree(ctx->d_timeline));
                 ctx->tl_cap = (size_t)(2 * n_node + 24) * 8 + 64;
                 CU(cudaMalloc((void**)&ctx->d_timeline, ctx->tl_cap * 8));
+                CU(cudaMemsetAsync(ctx->d_timeline, 0, ctx->tl_cap * 8, ctx->stream));     // (only here: a memset between the kernels of a step would sit on the measured path)
             }
-            CU(cudaMemsetAsync(ctx->d_timeline, 0, ctx->tl_cap * 8, ctx->stream));
             a.timeline = ctx->d_timeline; ctx->tl_n = (2 * n_node + 6) * 8;
         }
         prof.skip_to(3);
@@ -469,8 +469,12 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
             lc.attrs = at; lc.numAttrs = 1;
             CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, true, 1>, a));
         }
-        else if (stage) CU(launch_k(k_fused<FUSED_NW, true, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
-        else CU(launch_k(k_fused<FUSED_NW, false, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, n_dev != nullptr && !ctx->profiling, a));
+        else {
+            static const bool no_pdl_fused = getenv("DRA_NO_PDL") != nullptr;
+            const bool dep = n_dev != nullptr && !ctx->profiling && !no_pdl_fused;      // programmatic dependent of the compaction
+            if (stage) CU(launch_k(k_fused<FUSED_NW, true, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, dep, a));
+            else CU(launch_k(k_fused<FUSED_NW, false, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, dep, a));
+        }
         ctx->launches += 1;
         prof.mark();
         cudaError_t e = cudaGetLastError();

@@ -74,8 +74,10 @@ def test_resident_kernel_is_stopped_by_destroy(pkg, oracle):
     po = A.PinnedBuffer(w.n_out, R.OUT_DTYPE)
     assert c.allocate(pc.array, None, w.n_out, flags=A.F_FRESH_INVENTORY, out=po.array).tobytes() == ref.tobytes()
     t0 = time.perf_counter()
-    c.close()                                                          # EXIT command: the kernel leaves at once, not after the idle time-out
-    assert time.perf_counter() - t0 < 0.015
+    c.serve_stop()                                                     # EXIT command: the kernel leaves at once, not after the idle time-out
+    assert time.perf_counter() - t0 < 0.01
+    c.close()
+    assert time.perf_counter() - t0 < 0.1                                # (the idle time-out alone would be 20 ms + teardown)
     with A.Context(device=0) as d:                                     # the device is free again
         d.set_table(w.table); d.set_inventory(w.gpus, w.node_off)
         assert d.allocate(w.claims).tobytes() == ref.tobytes()
