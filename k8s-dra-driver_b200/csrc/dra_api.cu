@@ -380,7 +380,19 @@ struct AllocView {
     const uint32_t* n_dev = nullptr;      // device-side claim count (the claim list was compacted on the device)
     int have_off = -1;                    // -1: from d_out_off; else the CALLER's out_off convention (spec §1/§3)
     bool no_pdl_first = false;
+    const ShardArgs* sa = nullptr;        // the compaction that produces the claim list: launched by launch_allocate — as its
+    uint32_t sc_rows = 1; bool sc_flat = true;   // own kernel, or run inside k_fused when the shard takes the single-launch kernel
 };
+
+int launch_compaction(dra_ctx* ctx, const ShardArgs& sa, uint32_t sc_rows, bool sc_flat) {
+    if (!sc_flat) k_shard_compact<<<sa.n_tiles, 256, 0, ctx->stream>>>(sa);
+    else if (sc_rows == 1) k_shard_compact_flat<1><<<sa.n_tiles, 256, 0, ctx->stream>>>(sa);
+    else k_shard_compact_flat<8><<<sa.n_tiles, 256, 0, ctx->stream>>>(sa);
+    ctx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "shard compaction launch: %s", cudaGetErrorString(e));
+    return DRA_OK;
+}
 
 int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uint32_t* d_out_off,
                     uint2* d_out, uint32_t n_out, uint32_t flags, const PktGather* tail = nullptr, bool* tail_done = nullptr,
@@ -416,9 +428,10 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         // the gather tail has every CTA wait for its peers' packets: all CTAs of the grid must be resident at once.
         // Shared memory left over goes to the send queue (records leave for the peers while the pack still runs).
         bool tail_ok = tail != nullptr;
+        const bool want_in = view && view->sa;             // a compaction comes with this launch
         size_t launch_smem = fused_smem;
         uint32_t q_cap = 0;
-        if (tail_ok) {
+        if (tail_ok || want_in) {
             static const bool no_q = getenv("DRA_NO_SENDQ") != nullptr;
             const size_t room = fused_smem + 32 <= 225 * 1024 ? (225 * 1024 - fused_smem - 32) / 16 : 0;
             q_cap = no_q ? 0u : (uint32_t)std::min<size_t>(room, 2048);
@@ -429,10 +442,25 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
                 else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<FUSED_NW, false, 1>, FUSED_NW * 32, launch_smem));
                 ctx->tail_cap_smem = (int)launch_smem; ctx->tail_cap_stage = (int)stage; ctx->tail_cap_cta = nb * ctx->n_sm;
             }
-            tail_ok = (int)(n_node + 1) <= ctx->tail_cap_cta;
+            const bool resident = (int)(n_node + 1) <= ctx->tail_cap_cta;
+            tail_ok = tail_ok && resident;
+            // the compaction inside the kernel: one 1024-claim tile per CTA, then a grid barrier (needs every CTA resident).
+            // An experiment, off by default (DRA_SHARD_IN_KERNEL=1 turns it on): it saves the second launch but pays a
+            // cooperative launch and a grid barrier, and loses the overlap of this kernel's prologue with the compaction —
+            // measured at N = 2: 30.97 us per step against 29.02 us with the compaction as its own kernel + PDL
+            // (profiles/r02_inkernel_compaction.txt)
+            const bool want_inside = getenv("DRA_SHARD_IN_KERNEL") != nullptr;
+            if (want_in && resident && stage && want_inside && ctx->coop_ok && !ctx->profiling && view->sc_flat &&
+                (view->sa->n_claim + 256u * SC_IN_ROWS - 1) / (256u * SC_IN_ROWS) <= n_node + 1) {
+                a.sh = *view->sa; a.sh_on = 1;
+                a.sh.n_tiles = std::max(1u, (view->sa->n_claim + 256u * SC_IN_ROWS - 1) / (256u * SC_IN_ROWS));
+                if (!ctx->d_gbar) { CU(cudaMalloc((void**)&ctx->d_gbar, 64)); CU(cudaMemsetAsync(ctx->d_gbar, 0, 64, ctx->stream)); }
+                a.dio.gbar = ctx->d_gbar;
+            }
         }
+        if (want_in && !a.sh_on && (rc = launch_compaction(ctx, *view->sa, view->sc_rows, view->sc_flat))) return rc;
         if (tail_ok) { a.peer = *tail; a.q_cap = q_cap; if (tail_done) *tail_done = true; }
-        else launch_smem = fused_smem;
+        else if (!a.sh_on) launch_smem = fused_smem;
         // clusters of 8 CTAs + TMA multicast: measured slower (profiles/cluster_multicast_r01e.txt: 28.1 vs 18.8 us per batch),
         // kept as an opt-in experiment (DRA_CLUSTER=1)
         constexpr int CLS = 8;
@@ -471,8 +499,17 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         }
         else {
             static const bool no_pdl_fused = getenv("DRA_NO_PDL") != nullptr;
-            const bool dep = n_dev != nullptr && !ctx->profiling && !no_pdl_fused;      // programmatic dependent of the compaction
-            if (stage) CU(launch_k(k_fused<FUSED_NW, true, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, dep, a));
+            const bool dep = n_dev != nullptr && !ctx->profiling && !no_pdl_fused && !a.sh_on;      // programmatic dependent of the compaction
+            if (a.sh_on) {                                  // compaction inside: a grid barrier, so a cooperative launch
+                cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
+                lc.gridDim = dim3(n_node + 1); lc.blockDim = dim3(FUSED_NW * 32); lc.dynamicSmemBytes = launch_smem; lc.stream = ctx->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                if (stage) CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, true, 1>, a));
+                else CU(cudaLaunchKernelEx(&lc, k_fused<FUSED_NW, false, 1>, a));
+            }
+            else if (stage) CU(launch_k(k_fused<FUSED_NW, true, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, dep, a));
             else CU(launch_k(k_fused<FUSED_NW, false, 1>, dim3(n_node + 1), dim3(FUSED_NW * 32), launch_smem, ctx->stream, dep, a));
         }
         ctx->launches += 1;
@@ -482,6 +519,7 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
         return DRA_OK;
     }
 
+    if (view && view->sa && (rc = launch_compaction(ctx, *view->sa, view->sc_rows, view->sc_flat))) return rc;
     static const bool no_pdl = getenv("DRA_NO_PDL") != nullptr;
     const bool pdl = !no_pdl && !ctx->profiling;
     if ((rc = launch_sort(ctx, d_claims, n_claim, d_out_off, d_out, n_out, flags, prof, a.inv_src, pdl, n_node, d_node_off, n_dev))) return rc;
@@ -1518,12 +1556,10 @@ int dra_allocate_batch_global_device(dra_ctx* ctx, const dra_claim_rec* d_claims
         CU(cudaMemcpyAsync(ctx->d_sc_times, init, 16, cudaMemcpyHostToDevice, ctx->stream));
         sa.timeline = ctx->d_sc_times;
     }
-    if (!sc_flat) k_shard_compact<<<n_tiles, 256, 0, ctx->stream>>>(sa);
-    else if (sc_rows == 1) k_shard_compact_flat<1><<<n_tiles, 256, 0, ctx->stream>>>(sa);
-    else k_shard_compact_flat<8><<<n_tiles, 256, 0, ctx->stream>>>(sa);
-    ctx->launches += 1;
+    // (launched by launch_allocate: as its own kernel, or inside k_fused)
     // 2. the usual chain on the shard's view of the inventory, results at the claims' GLOBAL slots
     AllocView view; view.node_lo = ctx->shard_lo; view.n_node = n_local_node; view.n_dev = ctx->d_sc_counts; view.have_off = d_out_off != nullptr;
+    view.sa = &sa; view.sc_rows = sc_rows; view.sc_flat = sc_flat;
     bool tail_done = false;
     rc = launch_allocate(ctx, ctx->d_cclaims, cap, ctx->d_coff, table, n_out, flags, gather ? &g : nullptr, &tail_done, &view);
     if (rc) return rc;

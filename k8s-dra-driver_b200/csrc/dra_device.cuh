@@ -799,6 +799,7 @@ k_sorted_prep(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_nod
 // take_stray set (they come back INVALID, spec §3).  coff[j] = first GLOBAL OutRec slot of kept claim j.
 __device__ __forceinline__ unsigned long long globaltimer_ns();
 constexpr uint32_t SC_TILE = 2048;
+constexpr int SC_IN_ROWS = 4;             // in-kernel form: tiles of 1024 claims, one per CTA of k_fused
 struct ShardArgs {
     const uint4* claims; uint32_t n_claim; const uint32_t* out_off;
     uint32_t node_lo, node_hi, n_node_global, take_stray, have_off;
@@ -931,15 +932,14 @@ k_shard_compact(const ShardArgs a) {
 // claims, all CTAs resident), and no chain at all: a tile publishes its aggregate and then reads the aggregates of
 // ALL its predecessors at once (8 loads per lane in flight: 256 predecessors per L2 round trip), spinning only until the last of
 // them has published.
+// One tile (ROWS x 256 claims) by one CTA of 256 threads; used by the kernel below and, for shards that take the single-launch
+// kernel, INSIDE k_fused (one tile per CTA, then a grid barrier: no second launch at all).
 template <int ROWS>
-__global__ void __launch_bounds__(256, 4)             // <= 64 registers: >= 592 CTAs resident, every tile of a <= 2M-claim batch
-k_shard_compact_flat(const ShardArgs a) {
+__device__ __forceinline__ void shard_tile_flat(const ShardArgs& a, const uint32_t tile) {
     __shared__ uint32_t rowc[8 * ROWS], rows[8 * ROWS], pre_c, rs_s[PEER_MAX];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ltm = lanemask_lt();
-    pdl_trigger();
     if (a.timeline && tid == 0) atomicMin(a.timeline, globaltimer_ns());
     if (tid < PEER_MAX) rs_s[tid] = 0;
-    const uint32_t tile = blockIdx.x;
     const uint32_t w0 = tile * (256 * ROWS) + wid * (32 * ROWS);
     uint4 c[ROWS]; uint32_t keepm = 0, rk[ROWS], own_sl[ROWS];
     #pragma unroll
@@ -1040,6 +1040,13 @@ k_shard_compact_flat(const ShardArgs a) {
         a.coff[pos] = a.out_off ? __ldg(&a.out_off[i]) : i;
     }
     if (a.timeline) { __syncthreads(); if (tid == 0) atomicMax(a.timeline + 1, globaltimer_ns()); }
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(256, 4)             // <= 64 registers: >= 592 CTAs resident, every tile of a <= 2M-claim batch
+k_shard_compact_flat(const ShardArgs a) {
+    pdl_trigger();
+    shard_tile_flat<ROWS>(a, blockIdx.x);
 }
 
 // ====================================================================================================
@@ -1226,6 +1233,7 @@ struct PackArgs {
     const uint4* claims;          // claims in input order                             (k_fused)
     const uint32_t* out_off;      // first out slot per claim or NULL                  (k_fused)
     uint32_t n_claim;             //                                                   (k_fused)
+    ShardArgs sh; uint32_t sh_on; // sharded call, shard small enough: the compaction runs INSIDE this kernel (one tile per CTA)  (k_fused)
     uint32_t q_cap;               // multi-GPU: entries of the shared-memory send queue behind the staged claims (0: none) (k_fused)
     const uint32_t* n_dev;        // if set: the real number of claims (<= n_claim, which then only sizes the layout) (k_fused)
     const uint4* inv_src;         // inventory read from here ...
@@ -1826,7 +1834,14 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
     const uint32_t ng = g1 - g0;
     if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, b.inv_src + g0, ng * 16u, ibar);
     // sharded call: the claim list was compacted on the device by the kernel before this one; b.n_claim is its capacity
-    if (a.n_dev) pdl_wait();                                 // (launched as a programmatic dependent of the compaction)
+    if (a.sh_on) {
+        // ... or right here: one 1024-claim tile per CTA (cooperative launch), a grid barrier, and the list is there —
+        // no second launch; the table and inventory copies above are already in flight behind it
+        if (blockIdx.x < a.sh.n_tiles) shard_tile_flat<SC_IN_ROWS>(a.sh, blockIdx.x);
+        grid_barrier(a.dio.gbar, gridDim.x, a.err);
+        asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores (other SMs) -> bulk-copy reads
+    }
+    else if (a.n_dev) pdl_wait();                            // (launched as a programmatic dependent of the compaction)
     const uint32_t n_claim = a.n_dev ? min(b.n_claim, __ldcg(a.n_dev)) : b.n_claim;
     if (a.n_dev && __ldcg(a.n_dev) > b.n_claim) {            // laid out for fewer claims: touch nothing, tell everybody
         if (blockIdx.x == 0) {

@@ -21,9 +21,11 @@ def _make_world(pkg, world, flags=0):
     return ctxs
 
 
-@pytest.mark.parametrize("world,cfg_flags,seed", [(2, 0, 0), (4, 0, 1), (3, "nofused", 2), (2, 0, 3)])
-def test_sharded_global_batch(pkg, oracle, world, cfg_flags, seed):
+@pytest.mark.parametrize("world,cfg_flags,seed", [(2, 0, 0), (4, 0, 1), (3, "nofused", 2), (2, 0, 3), (2, "inkernel", 4), (4, "inkernel", 1)])
+def test_sharded_global_batch(pkg, oracle, world, cfg_flags, seed, monkeypatch):
     R = pkg.records
+    if cfg_flags == "inkernel":                                          # experiment: the compaction INSIDE k_fused (one launch per call)
+        monkeypatch.setenv("DRA_SHARD_IN_KERNEL", "1")
     flags = pkg.api.CFG_NO_FUSED if cfg_flags == "nofused" else 0
     w = pkg.synth.mixed(6000, 30, 60 + seed, invalid=seed != 3) if seed != 1 else pkg.synth.cfg2(8000, 40)
     out_off = w.out_off
@@ -43,9 +45,12 @@ def test_sharded_global_batch(pkg, oracle, world, cfg_flags, seed):
         d_off = None if out_off is None else _dev(out_off)
         ref, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, out_off, w.n_out)
         for rep in range(4):                                             # repeated calls: parity double-buffering, plan from the hint
+            l0 = ctxs[0].launch_count()
             for c in ctxs:                                               # enqueue on every rank, THEN wait
                 c.allocate_global_device(d_claims.data_ptr(), w.n_claim, None if d_off is None else d_off.data_ptr(), w.n_out,
                                          pkg.api.F_FRESH_INVENTORY)
+            if cfg_flags == "inkernel" and rep:
+                assert ctxs[0].launch_count() - l0 == 1, "the in-kernel compaction was not taken"
             for r, c in enumerate(ctxs):
                 got = c.gather_read(np.zeros(w.n_out, dtype=R.OUT_DTYPE))
                 assert got.tobytes() == ref.tobytes(), f"rank {r} rep {rep}: table differs from the oracle"
