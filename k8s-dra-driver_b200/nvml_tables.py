@@ -126,7 +126,9 @@ class Nvml:
     def gpu_instance_profile_info(self, device, i: int):
         info = _ProfileInfo()
         rc = self.lib.nvmlDeviceGetGpuInstanceProfileInfo(device, C.c_uint(i), C.byref(info))
-        return rc, {"id": int(info.id), "memory_size_mb": int(info.memorySizeMB), "slice_count": int(info.sliceCount)}
+        return rc, {"id": int(info.id), "memory_size_mb": int(info.memorySizeMB), "slice_count": int(info.sliceCount),
+                    "instance_count": int(info.instanceCount), "multiprocessor_count": int(info.multiprocessorCount),
+                    "copy_engine_count": int(info.copyEngineCount)}
 
     def gpu_instance_possible_placements(self, device, profile_id: int):
         n = C.c_uint(0)
