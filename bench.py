@@ -51,13 +51,15 @@ def workload(pkg, world: int):
     return w
 
 
-def config(world: int) -> dict:
+def config(world: int, aligned: bool = False) -> dict:
     return {"workload": "cfg2: 10k mixed 1g/2g/3g/7g MIG claims (40/30/20/10 %), unsorted, 125 nodes x 8 GPUs"
                         + (f"; x{world}: ONE global batch of {CLAIMS_PER_RANK * world} claims over {NODES_PER_RANK * world} nodes, node ranges "
                            f"sharded over {world} ranks on the device + all-gather of OutRecs" if world > 1 else ""),
             "claims": CLAIMS_PER_RANK * world, "gpus": NODES_PER_RANK * GPUS_PER_NODE * world,
             "nodes": NODES_PER_RANK * world, "parallelism": f"node-shard x{world}",
-            "l2": "flushed between steps (256 MiB write)", "inventory": "fresh per step (DRA_F_FRESH_INVENTORY)"}
+            "l2": "flushed between steps (256 MiB write)" + ("; ranks lined up on the device after each flush (untimed dra_peer_rendezvous_device), so a "
+                                                             "step does not time its peers' flush skew" if world > 1 and aligned else ""),
+            "inventory": "fresh per step (DRA_F_FRESH_INVENTORY)"}
 
 
 def peaks():
@@ -215,6 +217,7 @@ class Timer:
 
     def __init__(self, torch, dist, stream, dev, world, flush):
         self.torch, self.dist, self.stream, self.dev, self.world, self.flush = torch, dist, stream, dev, world, flush
+        self.align = None        # N > 1: device-side rendezvous of the ranks, enqueued between the flush and the timed step
 
     def barrier(self):
         if self.world > 1:
@@ -230,6 +233,8 @@ class Timer:
         self.barrier()
         for a, b in evs:
             self.flush.fill_(1)                   # L2 flush, outside the event pair
+            if self.align:                        # the ranks' 256 MiB flushes do not take the same time: without this a rank's
+                self.align()                      # event pair would also time its wait for the peer whose flush ran longest
             a.record(self.stream); step(); b.record(self.stream)
         self.barrier()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -285,6 +290,7 @@ def run_ours(args):
             hs = [None] * world
             dist.all_gather_object(hs, ctx.shard_export(wl.n_out))
             ctx.peer_import(hs)
+            timer.align = ctx.peer_rendezvous if args.align else None
 
     def make_step(wl, d_claims, d_out):
         if world > 1:
@@ -391,7 +397,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": dict(config(world), **({"collective": collective} if collective else {})),
+                "config": dict(config(world, args.align), **({"collective": collective} if collective else {})),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_claim,
                         "d2h_bytes_per_step": 8 * n_out, "timer": "host wall clock around the C-ABI call",
                         "us_per_batch": 1e6 * e2e_s / args.steps,
@@ -515,6 +521,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="e2e leg: enqueue H2D / kernel / D2H separately instead of one CUDA graph")
     ap.add_argument("--no-resident", action="store_true", help="e2e leg: one cooperative launch per batch instead of the resident kernel + doorbell")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (skip the other configs / calls)")
+    ap.add_argument("--align", action="store_true", help="N > 1: device-side rendezvous of the ranks (dra_peer_rendezvous_device) between the untimed L2 "
+                    "flush and the timed step; measured at N = 2: no difference (29.46 vs 29.48 us), off by default")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -300,6 +300,14 @@ int  dra_peer_import(dra_ctx* ctx, const void* handles);
 int  dra_comm_init_local(dra_ctx* ctx, int rank, int world);
 int  dra_peer_import_local(dra_ctx* ctx, dra_ctx* const* ctxs);
 
+/* Cross-rank rendezvous ON THE DEVICE: enqueues one tiny kernel on the context's stream that tells every peer "rank r is
+ * here" (one 4-byte store over NVLink each) and waits until every peer has said the same (after dra_peer_import /
+ * dra_peer_import_local; every rank must call it the same number of times; no host synchronisation, returns at once).
+ * It orders nothing but time: the ranks' streams leave it within one NVLink latency of each other.  bench.py calls it
+ * between its untimed L2 flush and the timed step, so that a rank's step does not absorb its peers' flush-time skew.
+ * A peer that never arrives within DRA_PEER_TIMEOUT_MS sets the context's error flag (next call: DRA_E_STATE). */
+int  dra_peer_rendezvous_device(dra_ctx* ctx);
+
 /* ---- sharded GLOBAL batch (BASELINE configs[2]: one batch, claim x node space sharded over the GPUs of a box) -----
  * Every rank loads the WHOLE inventory (dra_set_inventory) and serves a contiguous node range
  * (dra_set_shard; pool = node, nodes are never split: vendor/k8s.io/dynamic-resource-allocation/kubeletplugin/

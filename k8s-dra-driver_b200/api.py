@@ -58,6 +58,7 @@ SYMBOLS = {
     "dra_peer_import": (_i32, [_vp, _vp]),
     "dra_comm_init_local": (_i32, [_vp, _i32, _i32]),
     "dra_peer_import_local": (_i32, [_vp, _vp]),
+    "dra_peer_rendezvous_device": (_i32, [_vp]),
     "dra_set_shard": (_i32, [_vp, _u32, _u32, _i32]),
     "dra_set_shard_map": (_i32, [_vp, _vp, _i32]),
     "dra_shard_export": (_i32, [_vp, _u32, _u32, _vp]),
@@ -313,6 +314,10 @@ class Context:
     def comm_init(self, uid: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._check(self._lib.dra_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
+    def peer_rendezvous(self) -> None:
+        """Enqueue a device-side rendezvous of all ranks on this context's stream (dra_peer_rendezvous_device)."""
+        self._check(self._lib.dra_peer_rendezvous_device(self._h))
 
     def gather_read(self, out_all: np.ndarray) -> np.ndarray:
         """D2H of the last gather's table into out_all (OUT_DTYPE, world * n_per_rank); synchronises."""

@@ -118,6 +118,7 @@ struct dra_ctx {
     uint32_t* d_gbar = nullptr;             // grid barrier words
     int n_sm = 0, coop_ok = 0;
     int dio_cap_smem = -1, dio_cap_cta = 0; // co-resident CTA capacity of k_fused at dio_cap_smem bytes of shared memory
+    int pack4_occ = -1;              // resident CTAs of k_pack<4> per SM (occupancy query, once)
     int tail_cap_smem = -1, tail_cap_stage = -1, tail_cap_cta = 0;   // the same for the gather tail
     const void* dio_seen[3] = {nullptr, nullptr, nullptr};   // host pointers already checked to be device-visible as-is
 
@@ -145,7 +146,8 @@ struct dra_ctx {
     bool peer_ready = false;
     uint32_t peer_form = 0;                     // 1: per-rank slices [world][n_per]   2: global slots [tab_len]
     uint32_t peer_n_per = 0, peer_tab_len = 0, peer_cap = 0, peer_epoch = 0;
-    size_t peer_bytes = 0, off_table[2] = {0, 0}, off_stage[2] = {0, 0}, off_hdr[2] = {0, 0};
+    size_t peer_bytes = 0, off_table[2] = {0, 0}, off_stage[2] = {0, 0}, off_hdr[2] = {0, 0}, off_flags = 0;
+    uint32_t rendezvous_seq = 0;
     uint8_t* peer_local = nullptr;              // this rank's buffer (cudaMalloc, exported by IPC handle)
     uint8_t* peer_base[PEER_MAX] = {};          // every rank's buffer as mapped here
     bool peer_ipc[PEER_MAX] = {};               // mapped with cudaIpcOpenMemHandle (else: same process)
@@ -219,11 +221,18 @@ int grow_pinned(dra_ctx* ctx, uint8_t*& p, size_t& cap, size_t need) {
 }
 
 struct Tiling { uint32_t T, n_tiles; bool cta_wide; };
-Tiling tiling(uint32_t n_claim, uint32_t n_node) {
-    // CTA-wide tiles of 2048 claims (k_bucket_hist8) whenever 8 x (n_node+1) u16 counters fit in shared memory
+Tiling tiling(uint32_t n_claim, uint32_t n_node, int n_sm) {
+    // CTA-wide tiles (k_bucket_hist8) whenever 8 x (n_node+1) u16 counters fit in shared memory: 2048 claims, or — once
+    // such tiles would outnumber the SMs — the multiple of 2048 that fills the SMs once (<= 32768: ranks are u16)
     if ((size_t)8 * ((size_t)n_node + 2) * 2 <= 200 * 1024) {
-        uint32_t n_tiles = n_claim ? (n_claim + H8_TILE - 1) / H8_TILE : 1;
-        return {H8_TILE, n_tiles, true};
+        static const bool fixed = getenv("DRA_HIST_TILE_2048") != nullptr;           // experiment switch: the round-1 tiling
+        uint32_t T = H8_TILE;
+        static const char* force = getenv("DRA_HIST_TILE");                          // experiment switch: a given multiple of 2048
+        if (force && n_claim > (uint32_t)n_sm * H8_TILE) T = std::min<uint32_t>(32768u, std::max<uint32_t>(H8_TILE, (uint32_t)atoi(force) / H8_TILE * H8_TILE));
+        else if (!fixed && n_claim > (uint32_t)n_sm * H8_TILE)
+            T = std::min<uint32_t>(32768u, ((n_claim + (uint32_t)n_sm - 1) / (uint32_t)n_sm + H8_TILE - 1) / H8_TILE * H8_TILE);
+        uint32_t n_tiles = n_claim ? (n_claim + T - 1) / T : 1;
+        return {T, n_tiles, true};
     }
     uint32_t T = (n_claim + 63) / 64;
     T = (T + 31) & ~31u;
@@ -244,7 +253,7 @@ int ensure_batch(dra_ctx* ctx, uint32_t n_claim, uint32_t n_out, bool own_io) {
         ctx->cap_claims = ncap;
     }
     if (own_io) { int rc = grow(ctx, ctx->d_out, ctx->cap_out, need_o, 64); if (rc) return rc; }
-    Tiling t = tiling(n_claim, ctx->n_node);
+    Tiling t = tiling(n_claim, ctx->n_node, ctx->n_sm);
     size_t need_h = (size_t)t.n_tiles * (ctx->n_node + 1);
     int rc = grow(ctx, ctx->d_hist, ctx->cap_hist, need_h, 64);
     return rc;
@@ -337,17 +346,24 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
             ctx->launches += 1;
             prof.mark(); prof.skip_to(3);
         } else {
-            Tiling t = tiling(n_claim, n_node);
+            Tiling t = tiling(n_claim, n_node, ctx->n_sm);
             if (t.cta_wide) {
                 const size_t smem = (size_t)8 * (((size_t)n_node + 2) & ~(size_t)1) * 2;
                 if (smem > 48 * 1024 && ctx->hist8_smem_set < (int)smem) {
-                    CU(cudaFuncSetAttribute(k_bucket_hist8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CU(cudaFuncSetAttribute(k_bucket_hist8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CU(cudaFuncSetAttribute(k_bucket_hist8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     ctx->hist8_smem_set = (int)smem;
                 }
                 if (!ctx->d_ticket) { CU(cudaMalloc((void**)&ctx->d_ticket, 64)); CU(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream)); }
-                k_bucket_hist8<<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank, n_dev);
+                if (t.T == H8_TILE) k_bucket_hist8<false><<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank, n_dev, t.T);
+                else k_bucket_hist8<true><<<t.n_tiles, 256, smem, ctx->stream>>>(d_claims, n_claim, n_node, ctx->d_hist, ctx->d_rank, n_dev, t.T);
                 prof.mark();
-                CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 7) / 8), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
+                // the scan: a warp per node with every load in flight at once (latency), or — big matrices — coalesced rows
+                static const bool no_rows = getenv("DRA_SCAN_BY_NODE") != nullptr;
+                if (!no_rows && (size_t)t.n_tiles * (n_node + 1) > (size_t)512 * 1024)
+                    CU(launch_k(k_bucket_scan_rows, dim3((n_node + 1 + 31) / 32), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
+                else
+                    CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 7) / 8), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
                 prof.mark();
             } else {
                 if (n_dev) return fail(ctx, DRA_E_INVAL, "sharded call: node range too wide for the CTA-wide histogram");
@@ -528,7 +544,15 @@ int launch_allocate(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const
     a.claim_off = ctx->d_claim_off;
     if (n_node) {
         if (n_node <= (uint32_t)ctx->n_sm * 16u) CU(launch_k(k_pack<1>, dim3(n_node), dim3(32), pack_smem_bytes(1), ctx->stream, pdl, a));
-        else CU(launch_k(k_pack<4>, dim3(std::min((n_node + 3) / 4, (uint32_t)ctx->n_sm * 8u)), dim3(128), pack_smem_bytes(4), ctx->stream, pdl, a));
+        else {
+            // more nodes than warps can be resident: CTAs of 4 warps, exactly as many as fit at once, each warp walking nodes
+            if (ctx->pack4_occ < 0) {
+                int nb = 0;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pack<4>, 128, pack_smem_bytes(4)));
+                ctx->pack4_occ = std::max(1, nb);
+            }
+            CU(launch_k(k_pack<4>, dim3(std::min((n_node + 3) / 4, (uint32_t)(ctx->n_sm * ctx->pack4_occ))), dim3(128), pack_smem_bytes(4), ctx->stream, pdl, a));
+        }
         ctx->launches += 1;
     }
     prof.mark();
@@ -578,7 +602,8 @@ int raise_smem_limits(dra_ctx* ctx, int optin) {
     if ((rc = raise_one(ctx, k_fused<FUSED_NW, false, 1>, optin))) return rc;
     if ((rc = raise_one(ctx, k_fused<FUSED_NW, true, 8>, optin))) return rc;
     if ((rc = raise_one(ctx, k_bucket_small, optin))) return rc;
-    if ((rc = raise_one(ctx, k_bucket_hist8, optin))) return rc;
+    if ((rc = raise_one(ctx, k_bucket_hist8<false>, optin))) return rc;
+    if ((rc = raise_one(ctx, k_bucket_hist8<true>, optin))) return rc;
     if ((rc = raise_one(ctx, k_bucket_hist, optin))) return rc;
     if ((rc = raise_one(ctx, k_serve<FUSED_NW>, optin))) return rc;
     // The compaction runs right before the single-launch kernel, which wants the SM's L1/shared split at "all shared".  An SM
@@ -1276,6 +1301,7 @@ int peer_setup(dra_ctx* ctx, uint32_t form, uint32_t n_per, uint32_t tab_len, ui
     for (int p = 0; p < 2; ++p) ctx->off_table[p] = take((size_t)tab_len * 8 + 16);
     for (int p = 0; p < 2; ++p) ctx->off_stage[p] = take((size_t)ctx->world * cap * 16);
     for (int p = 0; p < 2; ++p) ctx->off_hdr[p] = take((size_t)ctx->world * 16);
+    ctx->off_flags = take((size_t)PEER_MAX * 4); ctx->rendezvous_seq = 0;
     ctx->peer_bytes = off;
     CU(cudaMalloc((void**)&ctx->peer_local, ctx->peer_bytes));
     CU(cudaMemset(ctx->peer_local, 0, ctx->peer_bytes));
@@ -1377,6 +1403,22 @@ int dra_peer_import_local(dra_ctx* ctx, dra_ctx* const* ctxs) {
         ctx->peer_base[r] = o->peer_local; ctx->peer_ipc[r] = false;
     }
     ctx->peer_ready = true;
+    return DRA_OK;
+}
+
+int dra_peer_rendezvous_device(dra_ctx* ctx) {
+    if (!ctx) return DRA_E_INVAL;
+    QUIESCE();
+    if (ctx->world <= 1) return DRA_OK;
+    if (!ctx->peer_ready) return fail(ctx, DRA_E_STATE, "dra_peer_import has not been called");
+    CU(cudaSetDevice(ctx->device));
+    RendezvousArgs a; memset(&a, 0, sizeof a);
+    for (int r = 0; r < ctx->world; ++r) a.peer_flags[r] = (uint32_t*)(ctx->peer_base[r] + ctx->off_flags);
+    a.my_flags = (const uint32_t*)(ctx->peer_local + ctx->off_flags);
+    a.world = (uint32_t)ctx->world; a.rank = (uint32_t)ctx->rank; a.seq = ++ctx->rendezvous_seq; a.spin_limit = ctx->peer_spin; a.err = err_of(ctx);
+    k_rendezvous<<<1, 32, 0, ctx->stream>>>(a);              // (not counted in dra_launch_count: it is no part of a batch)
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DRA_E_CUDA, "k_rendezvous: %s", cudaGetErrorString(e));
     return DRA_OK;
 }
 

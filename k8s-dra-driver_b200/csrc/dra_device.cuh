@@ -482,15 +482,67 @@ k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node,
 // Per-warp counters keep the pass stable (as k_bucket_small); all 8 keys of a lane are loaded before the first
 // is used.  hist[t][n] = claims of tile t on node n; rank[i] = stable rank of claim i inside its tile.
 constexpr uint32_t H8_TILE = 2048;
+template <bool MULTI>
 __global__ void __launch_bounds__(256)
 k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_node,
-               uint32_t* __restrict__ hist, uint16_t* __restrict__ rank, const uint32_t* __restrict__ n_dev) {
+               uint32_t* __restrict__ hist, uint16_t* __restrict__ rank, const uint32_t* __restrict__ n_dev, const uint32_t T) {
     extern __shared__ uint16_t cnt8[];                              // [8][nbp]
     pdl_trigger();
     if (n_dev) n_claim = min(n_claim, __ldcg(n_dev));               // sharded call: compacted on the device
     const uint32_t nb = n_node + 1, nbp = (nb + 1) & ~1u;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nbits = 32u - (uint32_t)__clz(n_node);
+    if (MULTI) {
+        // Large batches (T = m x 2048, chosen so that the tiles fill the SMs once): the per-tile work that is
+        // proportional to the number of NODES (clearing 8 counter rows, combining them, one hist row out — and a
+        // column of the matrix for the scan and the scatter to walk) is paid once per T claims instead of once per
+        // 2048.  A warp owns T/8 consecutive claims and walks them 8 rows at a time; the ranks inside the warp's part
+        // go out as they are found, the warp's base inside the tile is added in a second sweep (keys re-read: L2 hits).
+        const uint32_t per_warp = T >> 3, w0 = blockIdx.x * T + wid * per_warp;
+        for (uint32_t i = tid; i < 4 * nbp; i += 256) reinterpret_cast<uint32_t*>(cnt8)[i] = 0;
+        __syncthreads();
+        uint16_t* mycnt = cnt8 + wid * nbp;
+        for (uint32_t c0 = 0; c0 < per_warp; c0 += 256) {
+            uint32_t keys[8];
+            #pragma unroll
+            for (int r = 0; r < 8; ++r) { const uint32_t i = w0 + c0 + r * 32 + lane; keys[r] = i < n_claim ? __ldg(&claims[i]).y : 0xFFFFFFFFu; }
+            #pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t i = w0 + c0 + r * 32 + lane;
+                const bool act = i < n_claim;
+                const uint32_t key = act ? (keys[r] < n_node ? keys[r] : n_node) : 0xFFFFFFFFu;
+                const uint32_t m = peers_by_bits(key, nbits, act);
+                const uint32_t rk = (uint32_t)__popc(m & lanemask_lt());
+                uint32_t old = 0;
+                if (act) old = mycnt[key];
+                if (act) rank[i] = (uint16_t)(old + rk);
+                __syncwarp();
+                if (act && rk == 0) mycnt[key] = (uint16_t)(old + (uint32_t)__popc(m));
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        uint32_t* h = hist + (size_t)blockIdx.x * nb;
+        for (uint32_t n = tid; n < nb; n += 256) {
+            uint32_t run = 0;
+            #pragma unroll
+            for (uint32_t w = 0; w < 8; ++w) { const uint32_t v = cnt8[w * nbp + n]; cnt8[w * nbp + n] = (uint16_t)run; run += v; }
+            h[n] = run;
+        }
+        __syncthreads();
+        if (wid != 0)                                               // (warp 0's base is zero everywhere)
+            for (uint32_t c0 = 0; c0 < per_warp; c0 += 256) {
+                uint32_t keys[8];
+                #pragma unroll
+                for (int r = 0; r < 8; ++r) { const uint32_t i = w0 + c0 + r * 32 + lane; keys[r] = i < n_claim ? __ldg(&claims[i]).y : 0xFFFFFFFFu; }
+                #pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint32_t i = w0 + c0 + r * 32 + lane;
+                    if (i < n_claim) rank[i] = (uint16_t)(rank[i] + mycnt[keys[r] < n_node ? keys[r] : n_node]);
+                }
+            }
+        return;
+    }
     const uint32_t w0 = blockIdx.x * H8_TILE + wid * 256;
     uint32_t keys[8];
     #pragma unroll
@@ -530,6 +582,51 @@ k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_no
     }
 }
 
+// The last CTA of a scan kernel (256 threads): node totals in claim_off[0..nb) -> exclusive offsets, claim_off[nb] = sum.
+// Thread t owns a contiguous run of ceil(nb/256) nodes: one sweep to sum them (8 loads in flight), ONE block-wide scan of
+// the 256 sums, one sweep to write — the number of dependent round trips does not grow with the number of nodes (the
+// round-per-256-nodes form cost 20 us at 10k nodes).
+__device__ __forceinline__ void totals_to_offsets(uint32_t* __restrict__ claim_off, const uint32_t nb, uint32_t* wsum /* [9] shared */) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t per = (nb + 255) / 256, lo = min(nb, tid * per), hi = min(nb, lo + per);
+    uint32_t sum = 0, m = lo;
+    for (; m + 8 <= hi; m += 8) {
+        uint32_t v[8];
+        #pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(&claim_off[m + q]);
+        #pragma unroll
+        for (int q = 0; q < 8; ++q) sum += v[q];
+    }
+    for (; m < hi; ++m) sum += __ldcg(&claim_off[m]);
+    uint32_t x = sum;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, x, d); if (lane >= (uint32_t)d) x += y; }
+    __syncthreads();                                   // (wsum may still be read by a previous use)
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = lane < 8 ? wsum[lane] : 0u;
+        uint32_t ws = w;
+        #pragma unroll
+        for (int d = 1; d < 8; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, ws, d); if (lane >= (uint32_t)d) ws += y; }
+        __syncwarp();
+        if (lane < 8) wsum[lane] = ws - w;
+        if (lane == 7) wsum[8] = ws;
+    }
+    __syncthreads();
+    uint32_t run = wsum[wid] + (x - sum);
+    m = lo;
+    for (; m + 8 <= hi; m += 8) {
+        uint32_t v[8];
+        #pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(&claim_off[m + q]);
+        #pragma unroll
+        for (int q = 0; q < 8; ++q) { claim_off[m + q] = run; run += v[q]; }
+    }
+    for (; m < hi; ++m) { const uint32_t v = __ldcg(&claim_off[m]); claim_off[m] = run; run += v; }
+    if (tid == 0) claim_off[nb] = wsum[8];
+}
+
 // k_bucket_scan8: grid = ceil((n_node+1)/8) CTAs of 8 warps, WARP per node, lanes over the tiles: every load of a
 // node's column is in flight at once (the thread-per-node form walked the tiles in 7 dependent L2 round trips on 4
 // SMs), the prefix over the tiles is a warp scan by shuffles.  In place: hist[t][n] <- sum_{t'<t}; node totals go to
@@ -562,38 +659,67 @@ k_bucket_scan8(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node, u
         if (lane == 0) claim_off[n] = run;
     }
     __threadfence();
-    __shared__ uint32_t last_s, wsum[8], carry_s, total_s;
+    __shared__ uint32_t last_s, wsum[9];
     __syncthreads();
     if (tid == 0) last_s = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (!last_s) return;
-    if (tid == 0) { *ticket = 0; carry_s = 0; }
+    if (tid == 0) *ticket = 0;
+    __threadfence();
+    totals_to_offsets(claim_off, nb, wsum);
+}
+
+// k_bucket_scan_rows: the same scan for BIG matrices (n_tiles x nb beyond ~0.5M counters), where the warp-per-node form
+// above drags a 32-byte sector through L2 for every 4-byte counter, twice (1M claims on 10k nodes: 133 of the batch's
+// 233 us).  Here a CTA owns 32 consecutive nodes, lane = node, and every access is a coalesced 128-byte row piece:
+// warp w sums its share of the tiles (8 loads in flight), the warps' sums are combined in shared memory, and a second
+// sweep (L2 hits) writes the exclusive prefixes.  Node totals -> claim_off; the last CTA (ticket) makes them offsets.
+__global__ void __launch_bounds__(256)
+k_bucket_scan_rows(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node, uint32_t* __restrict__ claim_off,
+                   uint32_t* __restrict__ ticket) {
+    const uint32_t nb = n_node + 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ uint32_t part[8][32];
+    __shared__ uint32_t last_s, wsum[9];
+    pdl_trigger(); pdl_wait();
+    const uint32_t n = blockIdx.x * 32 + lane;
+    const uint32_t K = (n_tiles + 7) / 8, t_lo = min(n_tiles, wid * K), t_hi = min(n_tiles, t_lo + K);
+    uint32_t sum = 0;
+    if (n < nb) {
+        uint32_t t = t_lo;
+        for (; t + 8 <= t_hi; t += 8) {
+            uint32_t v[8];
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __ldcg(&hist[(size_t)(t + q) * nb + n]);
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) sum += v[q];
+        }
+        for (; t < t_hi; ++t) sum += __ldcg(&hist[(size_t)t * nb + n]);
+    }
+    part[wid][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+    #pragma unroll
+    for (uint32_t w = 0; w < 8; ++w) { const uint32_t v = part[w][lane]; run += w < wid ? v : 0u; total += v; }
+    if (n < nb) {
+        uint32_t t = t_lo;
+        for (; t + 8 <= t_hi; t += 8) {
+            uint32_t v[8];
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __ldcg(&hist[(size_t)(t + q) * nb + n]);
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) { hist[(size_t)(t + q) * nb + n] = run; run += v[q]; }
+        }
+        for (; t < t_hi; ++t) { const uint32_t v = __ldcg(&hist[(size_t)t * nb + n]); hist[(size_t)t * nb + n] = run; run += v; }
+        if (wid == 0) claim_off[n] = total;
+    }
     __threadfence();
     __syncthreads();
-    for (uint32_t n0 = 0; n0 < nb; n0 += 256) {
-        const uint32_t m = n0 + tid;
-        const uint32_t run = m < nb ? __ldcg(&claim_off[m]) : 0u;
-        uint32_t x = run;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, x, d); if (lane >= (uint32_t)d) x += y; }
-        if (lane == 31) wsum[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            const uint32_t w = lane < 8 ? wsum[lane] : 0u;
-            uint32_t ws = w;
-            #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, ws, d); if (lane >= (uint32_t)d) ws += y; }
-            if (lane < 8) wsum[lane] = ws - w;
-            if (lane == 7) total_s = ws;
-        }
-        __syncthreads();
-        const uint32_t excl = carry_s + wsum[wid] + (x - run);
-        if (m < nb) claim_off[m] = excl;
-        __syncthreads();
-        if (tid == 0) carry_s += total_s;
-        __syncthreads();
-    }
-    if (tid == 0) claim_off[nb] = carry_s;
+    if (tid == 0) last_s = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last_s) return;
+    if (tid == 0) *ticket = 0;
+    __threadfence();
+    totals_to_offsets(claim_off, nb, wsum);
 }
 
 // thread per claim.  sorted[dest] = claim with .y replaced by its first OutRec slot.
@@ -1047,6 +1173,25 @@ __global__ void __launch_bounds__(256, 4)             // <= 64 registers: >= 592
 k_shard_compact_flat(const ShardArgs a) {
     pdl_trigger();
     shard_tile_flat<ROWS>(a, blockIdx.x);
+}
+
+// Cross-rank rendezvous on the device (dra_peer_rendezvous_device): lane r stores this call's sequence number into peer
+// r's flag word for this rank, then every lane waits until its own peer's word for THIS rank has reached it.  Monotonic
+// sequence numbers: nothing is ever reset.  Orders nothing but time — it lines the ranks' streams up (a benchmark uses it
+// after its untimed L2 flush so that a rank's timed step does not absorb its peers' flush-duration skew).
+struct RendezvousArgs { uint32_t* peer_flags[PEER_MAX]; const uint32_t* my_flags; uint32_t world, rank, seq; long long spin_limit; Err err; };
+__global__ void __launch_bounds__(32)
+k_rendezvous(const RendezvousArgs a) {
+    const uint32_t lane = threadIdx.x;
+    if (lane >= a.world) return;
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[lane] + a.rank), "r"(a.seq) : "memory");
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.my_flags + lane) : "memory");
+        if ((int32_t)(v - a.seq) >= 0) break;
+        if (clock64() - t0 > a.spin_limit) { a.err.set(ERR_PEER_TIMEOUT); break; }
+    } while (true);
 }
 
 // ====================================================================================================
@@ -1832,7 +1977,7 @@ __device__ __forceinline__ void fused_body(const PackArgs& a, const Batch b, uin
     __syncthreads();
     if (threadIdx.x == 0) tma_load_a(sbase + FU_TBL, a.tbl, 1024u, tbar);
     const uint32_t ng = g1 - g0;
-    if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, b.inv_src + g0, ng * 16u, ibar);
+    if (threadIdx.x == 32 && ng) tma_load_a(sbase + FU_INV, b.inv_src + g0, ng * 16u, ibar);     // (issuing it after the claim pieces instead: measured, no gain)
     // sharded call: the claim list was compacted on the device by the kernel before this one; b.n_claim is its capacity
     if (a.sh_on) {
         // ... or right here: one 1024-claim tile per CTA (cooperative launch), a grid barrier, and the list is there —

@@ -75,6 +75,7 @@ for name, w, ctx_flags in [("global batch, fused, mixed", pkg.synth.mixed(9000, 
     d_off = None if w.out_off is None else torch.from_numpy(w.out_off.view(np.uint8).copy()).to(dev)
     ref, ref_inv = O.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
     for rep in range(3):
+        ctx.peer_rendezvous()                       # device-side rendezvous of the ranks (what bench.py enqueues after its flush)
         ctx.allocate_global_device(d_claims.data_ptr(), w.n_claim, None if d_off is None else d_off.data_ptr(), w.n_out, pkg.api.F_FRESH_INVENTORY)
         table = ctx.gather_read(np.zeros(w.n_out, dtype=R.OUT_DTYPE))
         g0, g1 = int(w.node_off[ranges[rank][0]]), int(w.node_off[ranges[rank][1]])

@@ -74,6 +74,15 @@ def test_cuda_matches_oracle_fuzz(pkg, ctx, oracle, seed):
     _assert_same(out, inv, ref_out, ref_inv, f"mixed seed {seed}")
 
 
+# ---- large batches: hist tiles that are multiples of 2048 (one wave of tiles), the row-wise scan of a big matrix ----
+@pytest.mark.parametrize("n_claim,n_node,kind", [(350_000, 6000, "mixed"), (700_000, 1200, "mixed"), (1_000_000, 10_000, "cfg2")])
+def test_large_batches_match_oracle(pkg, ctx, oracle, n_claim, n_node, kind):
+    w = pkg.synth.mixed(n_claim, n_node, 77, invalid=True) if kind == "mixed" else pkg.synth.cfg2(n_claim, n_node)
+    out, inv = _run(ctx, w)
+    ref_out, ref_inv = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
+    _assert_same(out, inv, ref_out, ref_inv, f"{kind} {n_claim} x {n_node}")
+
+
 # ---- the packers' fast loops: 64-bit SWAR node state (<= 8 GPUs x <= 8 slices) and the ballot form (wider) ----
 @pytest.mark.parametrize("seed,model,wide16,max_width", [
     (0, 0, False, 8), (1, 0, False, 32), (2, 1, False, 8), (3, 0, True, 8), (4, 0, True, 32), (5, 1, False, 32),

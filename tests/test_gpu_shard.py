@@ -140,3 +140,30 @@ def test_per_rank_slices_gather(pkg, oracle, world, nofused):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_device_rendezvous_of_world_contexts(pkg):
+    """dra_peer_rendezvous_device: every rank enqueues it, nobody waits on the host in between; repeated calls use
+    increasing sequence numbers (nothing to reset); world 1 is a no-op."""
+    import torch
+    w = pkg.synth.cfg2(2000, 8)
+    ctxs = _make_world(pkg, 3)
+    try:
+        for c in ctxs:
+            c.set_table(w.table); c.set_inventory(w.gpus, w.node_off); c.set_shard_map([0, 3, 6, 8], stray_rank=0)
+            c.shard_export(w.n_out, 0, want_handle=False)
+        for c in ctxs:
+            c.peer_import_local(ctxs)
+        for _ in range(5):
+            l0 = ctxs[1].launch_count()
+            for c in ctxs:
+                c.peer_rendezvous()
+            assert ctxs[1].launch_count() == l0       # (no part of a batch: not counted)
+        for c in ctxs:
+            c.sync()
+        torch.cuda.synchronize()
+    finally:
+        for c in ctxs:
+            c.close()
+    with pkg.api.Context(device=0) as c:
+        c.peer_rendezvous()                      # world 1: nothing to do
