@@ -118,6 +118,7 @@ struct dra_ctx {
     uint32_t* d_gbar = nullptr;             // grid barrier words
     int n_sm = 0, coop_ok = 0;
     int dio_cap_smem = -1, dio_cap_cta = 0; // co-resident CTA capacity of k_fused at dio_cap_smem bytes of shared memory
+    unsigned long long* d_scan_status = nullptr; uint32_t cap_scan_status = 0;   // k_bucket_scan_rows: one word per CTA
     int pack4_occ = -1;              // resident CTAs of k_pack<4> per SM (occupancy query, once)
     int tail_cap_smem = -1, tail_cap_stage = -1, tail_cap_cta = 0;   // the same for the gather tail
     const void* dio_seen[3] = {nullptr, nullptr, nullptr};   // host pointers already checked to be device-visible as-is
@@ -360,8 +361,18 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
                 prof.mark();
                 // the scan: a warp per node with every load in flight at once (latency), or — big matrices — coalesced rows
                 static const bool no_rows = getenv("DRA_SCAN_BY_NODE") != nullptr;
-                if (!no_rows && (size_t)t.n_tiles * (n_node + 1) > (size_t)512 * 1024)
-                    CU(launch_k(k_bucket_scan_rows, dim3((n_node + 1 + 31) / 32), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
+                if (!no_rows && (size_t)t.n_tiles * (n_node + 1) > (size_t)512 * 1024) {
+                    const uint32_t n_cta = (n_node + 1 + 31) / 32;
+                    if (ctx->cap_scan_status < n_cta) {                  // (one status word per CTA: grown outside the hot path)
+                        CU(cudaStreamSynchronize(ctx->stream));
+                        if (ctx->d_scan_status) CU(cudaFree(ctx->d_scan_status));
+                        ctx->cap_scan_status = n_cta + n_cta / 2 + 64;
+                        CU(cudaMalloc((void**)&ctx->d_scan_status, (size_t)ctx->cap_scan_status * 8));
+                        CU(cudaMemsetAsync(ctx->d_scan_status, 0, (size_t)ctx->cap_scan_status * 8, ctx->stream));
+                        ctx->state_epoch++;
+                    }
+                    CU(launch_k(k_bucket_scan_rows, dim3(n_cta), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 10, ctx->d_scan_status, err));
+                }
                 else
                     CU(launch_k(k_bucket_scan8, dim3((n_node + 1 + 7) / 8), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 8));
                 prof.mark();
@@ -780,6 +791,7 @@ void dra_ctx_destroy(dra_ctx* c) {
     for (int r = 0; r < (int)PEER_MAX; ++r) if (c->peer_base[r] && c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->peer_local) cudaFree(c->peer_local);
     if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_scan_status) cudaFree(c->d_scan_status);
     if (c->d_gbar) cudaFree(c->d_gbar);
     void* dev[] = {c->d_inv_live, c->d_inv_pristine, c->d_node_off, c->d_tbl, c->d_claims, c->d_sorted, c->d_out_off,
                    c->d_out, c->d_rank, c->d_hist, c->d_claim_off, c->d_pod_off, c->d_cand_off, c->d_cand_nodes,

@@ -502,6 +502,7 @@ k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_no
         for (uint32_t i = tid; i < 4 * nbp; i += 256) reinterpret_cast<uint32_t*>(cnt8)[i] = 0;
         __syncthreads();
         uint16_t* mycnt = cnt8 + wid * nbp;
+        uint32_t* row32 = reinterpret_cast<uint32_t*>(mycnt);             // (nbp is even: every warp's row starts on a word)
         for (uint32_t c0 = 0; c0 < per_warp; c0 += 256) {
             uint32_t keys[8];
             #pragma unroll
@@ -510,14 +511,21 @@ k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_no
             for (int r = 0; r < 8; ++r) {
                 const uint32_t i = w0 + c0 + r * 32 + lane;
                 const bool act = i < n_claim;
-                const uint32_t key = act ? (keys[r] < n_node ? keys[r] : n_node) : 0xFFFFFFFFu;
-                const uint32_t m = peers_by_bits(key, nbits, act);
-                const uint32_t rk = (uint32_t)__popc(m & lanemask_lt());
+                const uint32_t key = act ? (keys[r] < n_node ? keys[r] : n_node) : 0u;
+                // the row's 32 keys are almost always distinct (32 of thousands of nodes): a shared-memory atomic on the
+                // u16 counter (the half of a 32-bit word) hands every lane its rank in one instruction; only if two lanes
+                // of the row share a key — the count grew by more than one — does the hardware's order among them have
+                // to be replaced by lane order, with the votes that otherwise cost ~70 instructions per row
+                const uint32_t sh = (key & 1u) << 4;
                 uint32_t old = 0;
-                if (act) old = mycnt[key];
-                if (act) rank[i] = (uint16_t)(old + rk);
+                if (act) old = (atomicAdd(&row32[key >> 1], 1u << sh) >> sh) & 0xFFFFu;
                 __syncwarp();
-                if (act && rk == 0) mycnt[key] = (uint16_t)(old + (uint32_t)__popc(m));
+                const uint32_t now = act ? (row32[key >> 1] >> sh) & 0xFFFFu : 0u;
+                if (__any_sync(FULLMASK, act && now != old + 1u)) {
+                    const uint32_t m = peers_by_bits(key, nbits, act);
+                    old = now - (uint32_t)__popc(m) + (uint32_t)__popc(m & lanemask_lt());
+                }
+                if (act) rank[i] = (uint16_t)old;
                 __syncwarp();
             }
         }
@@ -676,11 +684,13 @@ k_bucket_scan8(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node, u
 // sweep (L2 hits) writes the exclusive prefixes.  Node totals -> claim_off; the last CTA (ticket) makes them offsets.
 __global__ void __launch_bounds__(256)
 k_bucket_scan_rows(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_node, uint32_t* __restrict__ claim_off,
-                   uint32_t* __restrict__ ticket) {
+                   uint32_t* __restrict__ ticket, unsigned long long* __restrict__ status, Err err) {
     const uint32_t nb = n_node + 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     __shared__ uint32_t part[8][32];
-    __shared__ uint32_t last_s, wsum[9];
     pdl_trigger(); pdl_wait();
+    // this launch's epoch: a device word that the LAST CTA to finish advances (so a replayed CUDA graph gets a new one too);
+    // nobody can have advanced it before every CTA has read it, because the last ticket is taken after all of them started
+    const uint32_t epoch = __ldcg(ticket + 1) + 1u;
     const uint32_t n = blockIdx.x * 32 + lane;
     const uint32_t K = (n_tiles + 7) / 8, t_lo = min(n_tiles, wid * K), t_hi = min(n_tiles, t_lo + K);
     uint32_t sum = 0;
@@ -700,6 +710,40 @@ k_bucket_scan_rows(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_nod
     uint32_t run = 0, total = 0;
     #pragma unroll
     for (uint32_t w = 0; w < 8; ++w) { const uint32_t v = part[w][lane]; run += w < wid ? v : 0u; total += v; }
+    if (wid == 0) {
+        // node totals -> claim offsets without a serial tail: this CTA publishes the sum of its 32 nodes and adds up the
+        // sums of ALL its predecessors (every load in flight at once, spinning only until the last of them is there)
+        uint32_t x = total;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, x, d); if (lane >= (uint32_t)d) x += y; }
+        const uint32_t agg = __shfl_sync(FULLMASK, x, 31);
+        if (lane == 0) atomicExch(&status[blockIdx.x], ((unsigned long long)epoch << 32) | agg);
+        uint32_t base = 0;
+        const long long t0 = clock64();
+        bool dead = false;
+        for (uint32_t b0 = 0; b0 < blockIdx.x && !dead; b0 += 256) {
+            unsigned long long v[8];
+            bool ready;
+            do {
+                ready = true;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t idx = b0 + k * 32 + lane;
+                    v[k] = 0;
+                    if (idx < blockIdx.x) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(status + idx) : "memory");
+                }
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) if (b0 + k * 32 + lane < blockIdx.x && (uint32_t)(v[k] >> 32) != epoch) ready = false;
+                if (clock64() - t0 > 2000000000ll) dead = true;
+            } while (!__all_sync(FULLMASK, ready || dead));
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) if (b0 + k * 32 + lane < blockIdx.x) base += (uint32_t)v[k];
+        }
+        base = __reduce_add_sync(FULLMASK, base);
+        if (dead && lane == 0) err.set(ERR_PEER_TIMEOUT);
+        if (n < nb) claim_off[n] = base + x - total;
+        if (blockIdx.x == gridDim.x - 1 && lane == 31) claim_off[nb] = base + agg;
+    }
     if (n < nb) {
         uint32_t t = t_lo;
         for (; t + 8 <= t_hi; t += 8) {
@@ -710,16 +754,9 @@ k_bucket_scan_rows(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_nod
             for (int q = 0; q < 8; ++q) { hist[(size_t)(t + q) * nb + n] = run; run += v[q]; }
         }
         for (; t < t_hi; ++t) { const uint32_t v = __ldcg(&hist[(size_t)t * nb + n]); hist[(size_t)t * nb + n] = run; run += v; }
-        if (wid == 0) claim_off[n] = total;
     }
-    __threadfence();
     __syncthreads();
-    if (tid == 0) last_s = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (!last_s) return;
-    if (tid == 0) *ticket = 0;
-    __threadfence();
-    totals_to_offsets(claim_off, nb, wsum);
+    if (tid == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0; __threadfence(); atomicAdd(ticket + 1, 1u); }
 }
 
 // thread per claim.  sorted[dest] = claim with .y replaced by its first OutRec slot.
