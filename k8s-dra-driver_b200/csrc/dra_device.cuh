@@ -558,20 +558,25 @@ k_bucket_hist8(const uint4* __restrict__ claims, uint32_t n_claim, uint32_t n_no
     for (uint32_t i = tid; i < 4 * nbp; i += 256) reinterpret_cast<uint32_t*>(cnt8)[i] = 0;
     __syncthreads();
     uint16_t* mycnt = cnt8 + wid * nbp;
+    uint32_t* row32 = reinterpret_cast<uint32_t*>(mycnt);
     uint32_t local[8];
     #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const uint32_t i = w0 + r * 32 + lane;
         const bool act = i < n_claim;
-        const uint32_t key = act ? (keys[r] < n_node ? keys[r] : n_node) : 0xFFFFFFFFu;
+        const uint32_t key = act ? (keys[r] < n_node ? keys[r] : n_node) : 0u;
         keys[r] = key;
-        const uint32_t m = peers_by_bits(key, nbits, act);
-        const uint32_t rk = (uint32_t)__popc(m & lanemask_lt());
+        // (as above: an atomic on the u16 half-word gives the rank; votes only for a row in which two lanes share a node)
+        const uint32_t sh = (key & 1u) << 4;
         uint32_t old = 0;
-        if (act) old = mycnt[key];
-        local[r] = old + rk;
+        if (act) old = (atomicAdd(&row32[key >> 1], 1u << sh) >> sh) & 0xFFFFu;
         __syncwarp();
-        if (act && rk == 0) mycnt[key] = (uint16_t)(old + (uint32_t)__popc(m));
+        const uint32_t now = act ? (row32[key >> 1] >> sh) & 0xFFFFu : 0u;
+        if (__any_sync(FULLMASK, act && now != old + 1u)) {
+            const uint32_t m = peers_by_bits(key, nbits, act);
+            old = now - (uint32_t)__popc(m) + (uint32_t)__popc(m & lanemask_lt());
+        }
+        local[r] = old;
         __syncwarp();
     }
     __syncthreads();
