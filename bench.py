@@ -454,8 +454,10 @@ def run_extras(pkg, O, ctx, timer, torch, dev, world, rank, load, make_step, res
             if not ok:
                 raise SystemExit(f"bench: {wl.name}: CUDA result differs from the oracle")
         ms = timer.run(step, steps, 3)
+        ab = wl.algorithmic_bytes()                                     # 16 B/claim + 16 B/GPU + 8 B/slot
         return {"claims": wl.n_claim, "gpus": wl.n_gpu, "nodes": wl.n_node, "us_per_batch": ms * 1e3,
-                "alloc_per_s": wl.n_claim / (ms * 1e-3), "kernel_launches_per_batch": per, "parity": "bit-exact vs oracle"}
+                "alloc_per_s": wl.n_claim / (ms * 1e-3), "kernel_launches_per_batch": per, "parity": "bit-exact vs oracle",
+                "algorithmic_bytes": ab, "hbm_frac_whole_step": ab / (ms * 1e-3) / 1e9 / peaks()[0]}
 
     cfgs = {}
     if world == 1:

@@ -18,3 +18,5 @@ echo "== memcheck(smoke) with PDL, for the record"; timeout 600 compute-sanitize
 echo "== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${T}_launches.csv python bench.py --steps 6 --warmup 3 --no-extras --no-resident > $O/${T}_ncu_bench.log 2>&1; grep -c "dra::" $O/${T}_launches.csv
 echo "== ncu full: k_fused"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 3 -c 1 -f -o $O/prof_${T}_fused python profiles/one_batch.py > $O/${T}_ncu_full.log 2>&1; ls -la $O/prof_${T}_fused.ncu-rep
 echo "== ncu full: sort path, k_unsuitable, shard compaction"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_bucket|k_pack|k_unsuitable|k_shard|k_fused" -s 4 -c 10 -f -o $O/prof_${T}_others python profiles/one_batch_sort.py > $O/${T}_ncu_others.log 2>&1; ls -la $O/prof_${T}_others.ncu-rep
+echo "== sort-path stage times (cfg3, cfg5, 1M)"; timeout 300 python profiles/stage_times.py 2>&1 | tail -3 | tee $O/${T}_stage_times.txt
+echo "== ncu full: large batch (1M claims)"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_bucket|k_pack" -s 8 -c 4 -f -o $O/prof_${T}_large python profiles/one_batch_large.py > $O/${T}_ncu_large.log 2>&1; ls -la $O/prof_${T}_large.ncu-rep
