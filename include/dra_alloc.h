@@ -296,7 +296,9 @@ int  dra_peer_import(dra_ctx* ctx, const void* handles);
 /* The same mapping for contexts of ONE process (one Go driver process driving all GPUs of a box, or tests): instead of
  * NCCL + IPC handles, call dra_comm_init_local(ctx, rank, world) on every context, dra_peer_export / dra_shard_export
  * (handle may be NULL), then dra_peer_import_local(ctx, ctxs) with the world contexts in rank order (peer access between
- * their devices is enabled here).  Calls of different ranks must then be issued without waiting for each other. */
+ * their devices is enabled here).  Calls of different ranks must then be issued without waiting for each other.
+ * One context per DEVICE is the supported layout; several ranks on one device work for batches that take the
+ * single-launch kernel (the tests do it) but can starve each other on the sort path (a waiting gather holds the SMs). */
 int  dra_comm_init_local(dra_ctx* ctx, int rank, int world);
 int  dra_peer_import_local(dra_ctx* ctx, dra_ctx* const* ctxs);
 

@@ -60,7 +60,9 @@ for name, w, ctx_flags, use_peer in [
 # ---- the sharded GLOBAL batch: the same claim array on every rank, device-side range filter, global slots ----
 for name, w, ctx_flags in [("global batch, fused, mixed", pkg.synth.mixed(9000, 97, 31), 0),
                            ("global batch, sort path", pkg.synth.mixed(30000, 200, 32), pkg.api.CFG_NO_FUSED),
-                           ("global batch, cfg3/4", pkg.synth.cfg2(25000, 250), 0)]:
+                           ("global batch, cfg3/4", pkg.synth.cfg2(25000, 250), 0),
+                           # large: every shard goes through wave-sized hist tiles, the row-wise scan and the stand-alone gather
+                           ("global batch, 1M claims x 10k nodes", pkg.synth.cfg2(1_000_000, 10_000), 0)]:
     ranges = pkg.shard.plan(w.claims["node"], w.n_node, world)
     ctx = pkg.api.Context(device=local, stream=stream.cuda_stream, flags=ctx_flags)
     ctx.set_table(w.table); ctx.set_inventory(w.gpus, w.node_off)

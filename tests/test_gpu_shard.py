@@ -167,3 +167,8 @@ def test_device_rendezvous_of_world_contexts(pkg):
             c.close()
     with pkg.api.Context(device=0) as c:
         c.peer_rendezvous()                      # world 1: nothing to do
+
+
+# (A LARGE sharded batch — wave-sized hist tiles, row-wise scan, stand-alone gather — is checked on real ranks only:
+#  tests/multi_gpu_check.py, "1M claims x 10k nodes".  Two contexts on ONE device cannot run it: a rank's gather kernel holds
+#  every SM at the default shared-memory split while it waits for its peer, whose histogram CTAs need the SMs re-split.)
