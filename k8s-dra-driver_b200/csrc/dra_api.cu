@@ -257,7 +257,20 @@ int ensure_batch(dra_ctx* ctx, uint32_t n_claim, uint32_t n_out, bool own_io) {
     Tiling t = tiling(n_claim, ctx->n_node, ctx->n_sm);
     size_t need_h = (size_t)t.n_tiles * (ctx->n_node + 1);
     int rc = grow(ctx, ctx->d_hist, ctx->cap_hist, need_h, 64);
-    return rc;
+    if (rc) return rc;
+    // k_bucket_scan_rows: one status word per CTA of 32 nodes, zeroed once (here, never inside a stream capture)
+    const uint32_t n_cta = (ctx->n_node + 1 + 31) / 32;
+    if (ctx->cap_scan_status < n_cta) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_scan_status) CU(cudaFree(ctx->d_scan_status));
+        ctx->d_scan_status = nullptr; ctx->cap_scan_status = 0;
+        const uint32_t ncap = n_cta + n_cta / 2 + 64;
+        CU(cudaMalloc((void**)&ctx->d_scan_status, (size_t)ncap * 8));
+        CU(cudaMemset(ctx->d_scan_status, 0, (size_t)ncap * 8));
+        ctx->cap_scan_status = ncap;
+        ctx->state_epoch++;
+    }
+    return DRA_OK;
 }
 
 SelCtx sel_of(dra_ctx* ctx) { return SelCtx{ctx->n_attr == ctx->n_gpu ? ctx->d_attrs : nullptr, ctx->d_sels, ctx->n_sel}; }
@@ -363,14 +376,7 @@ int launch_sort(dra_ctx* ctx, const uint4* d_claims, uint32_t n_claim, const uin
                 static const bool no_rows = getenv("DRA_SCAN_BY_NODE") != nullptr;
                 if (!no_rows && (size_t)t.n_tiles * (n_node + 1) > (size_t)512 * 1024) {
                     const uint32_t n_cta = (n_node + 1 + 31) / 32;
-                    if (ctx->cap_scan_status < n_cta) {                  // (one status word per CTA: grown outside the hot path)
-                        CU(cudaStreamSynchronize(ctx->stream));
-                        if (ctx->d_scan_status) CU(cudaFree(ctx->d_scan_status));
-                        ctx->cap_scan_status = n_cta + n_cta / 2 + 64;
-                        CU(cudaMalloc((void**)&ctx->d_scan_status, (size_t)ctx->cap_scan_status * 8));
-                        CU(cudaMemsetAsync(ctx->d_scan_status, 0, (size_t)ctx->cap_scan_status * 8, ctx->stream));
-                        ctx->state_epoch++;
-                    }
+                    if (ctx->cap_scan_status < n_cta) return fail(ctx, DRA_E_STATE, "scan status words not allocated (ensure_batch)");
                     CU(launch_k(k_bucket_scan_rows, dim3(n_cta), dim3(256), 0, ctx->stream, pdl, ctx->d_hist, t.n_tiles, n_node, ctx->d_claim_off, ctx->d_ticket + 10, ctx->d_scan_status, err));
                 }
                 else

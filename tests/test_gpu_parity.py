@@ -83,6 +83,23 @@ def test_large_batches_match_oracle(pkg, ctx, oracle, n_claim, n_node, kind):
     _assert_same(out, inv, ref_out, ref_inv, f"{kind} {n_claim} x {n_node}")
 
 
+def test_large_batch_through_a_replayed_graph(pkg, oracle):
+    """The row-wise scan finds its predecessors' sums by an epoch that the kernel itself advances on the device: a captured
+    graph replays with the same arguments and must still see a fresh epoch every time (eager, capture, replay, replay)."""
+    R = pkg.records
+    w = pkg.synth.cfg2(600_000, 6000)
+    ref, _ = oracle.allocate(w.gpus, w.node_off, w.table, w.claims, threads=8)
+    with pkg.api.Context(device=0, flags=pkg.api.CFG_USE_GRAPH | pkg.api.CFG_NO_DIRECT) as g:
+        g.set_table(w.table); g.set_inventory(w.gpus, w.node_off)
+        pc = pkg.api.PinnedBuffer(w.n_claim, R.CLAIM_DTYPE); pc.array[:] = w.claims
+        po = pkg.api.PinnedBuffer(w.n_out, R.OUT_DTYPE)
+        for it in range(5):
+            po.array[:] = 0
+            g.allocate(pc.array, None, w.n_out, flags=pkg.api.F_FRESH_INVENTORY, out=po.array)
+            assert po.array.tobytes() == ref.tobytes(), it
+        pc.free(); po.free()
+
+
 # ---- the packers' fast loops: 64-bit SWAR node state (<= 8 GPUs x <= 8 slices) and the ballot form (wider) ----
 @pytest.mark.parametrize("seed,model,wide16,max_width", [
     (0, 0, False, 8), (1, 0, False, 32), (2, 1, False, 8), (3, 0, True, 8), (4, 0, True, 32), (5, 1, False, 32),
