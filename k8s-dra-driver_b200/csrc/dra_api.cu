@@ -1158,6 +1158,8 @@ int dra_unsuitable_batch(dra_ctx* ctx, const dra_claim_rec* claims, uint32_t n_c
         const uint32_t per_cta = 8 * (32 / W);
         const uint32_t grid = std::max(1u, std::min((n_pair + per_cta - 1) / per_cta, (uint32_t)ctx->n_sm * 8u));
         if (a.exhaustive) {
+            a.work = ctx->d_ticket + 12;
+            CU(cudaMemsetAsync(a.work, 0, 4, ctx->stream));
             if (W == 8) k_unsuitable<8, 8, true><<<grid, 256, 0, ctx->stream>>>(a);
             else if (W == 16) k_unsuitable<8, 16, true><<<grid, 256, 0, ctx->stream>>>(a);
             else k_unsuitable<8, 32, true><<<grid, 256, 0, ctx->stream>>>(a);

@@ -2660,6 +2660,8 @@ struct UnsArgs {
     SelCtx sel;
     uint32_t dense;     // 1: every pod x every node, pair = pod * n_node + node (cand arrays unused)
     uint32_t exhaustive; // spec §12: pod evaluation with the backtracking search
+    uint32_t* work;      // EXH: next unclaimed pair (zeroed by the caller) — searches differ by orders of magnitude in length,
+                         //      so the warps take their pairs from a counter instead of a fixed stride
 };
 
 struct GlobalGet {
@@ -2681,7 +2683,13 @@ k_unsuitable(const UnsArgs a) {
     const uint32_t grp = lane / W, gl = lane % W, gbase = grp * W;
     const uint32_t gmask = W == 32 ? FULLMASK : (((1u << (W & 31)) - 1u) << gbase);
     const uint32_t stride = gridDim.x * WPC * G;
-    for (uint32_t pw = (blockIdx.x * WPC + wid) * G; pw < a.n_pair; pw += stride) {
+    for (uint32_t pw = (blockIdx.x * WPC + wid) * G; ; pw += stride) {
+        if (EXH) {
+            uint32_t nxt = 0;
+            if (lane == 0) nxt = atomicAdd(a.work, G);
+            pw = __shfl_sync(FULLMASK, nxt, 0);
+        }
+        if (pw >= a.n_pair) break;
         const uint32_t pair = pw + grp;
         if (pair >= a.n_pair) continue;                                  // whole group skips together
         uint32_t pod, node;

@@ -14,8 +14,10 @@ with A.Context(device=0) as ctx:
                      ("allocate_pods first-fit (same pods)", lambda: ctx.allocate_pods(pw.claims, ppo, flags=A.F_FRESH_INVENTORY)),
                      ("unsuitable exhaustive, 4000 pods x 64 nodes", lambda: ctx.unsuitable(pc, po, flags=A.F_EXHAUSTIVE)),
                      ("unsuitable first-fit, 4000 pods x 64 nodes", lambda: ctx.unsuitable(pc, po))):
+        ctx.set_inventory(pw.gpus, pw.node_off)       # every measurement against the same (pre-fragmented, otherwise free) inventory
         ts = []
         for _ in range(6):
             t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        ctx.set_inventory(pw.gpus, pw.node_off)
         ctx.set_profiling(True); fn(); k = {a: round(b, 1) for a, b in ctx.timings_us().items() if b > 0}; ctx.set_profiling(False)
         print(f"{name:<62} first call {ts[0] * 1e3:7.2f} ms, then median {statistics.median(ts[1:]) * 1e3:7.2f} ms; kernels (us): {k}")
