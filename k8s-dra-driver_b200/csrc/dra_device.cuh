@@ -30,6 +30,7 @@ constexpr uint32_t RING = 4;          // ring slots per warp
 constexpr uint32_t ERR_OUT_RANGE = 1u;    // index into the error-flag words
 constexpr uint32_t ERR_NOT_SORTED = 2u;
 constexpr uint32_t ERR_PEER_TIMEOUT = 3u;
+constexpr uint32_t ERR_DEVICE_WAIT = 5u;     // a wait inside ONE GPU gave up (grid barrier, look-back): cannot happen unless CTAs were not co-scheduled
 constexpr uint32_t ERR_SHARD_PLAN = 4u;      // sharded call: more claims fell into this shard than the launch was laid out for
 constexpr uint32_t ERR_WORDS = 8u;
 constexpr uint32_t PEER_MAX = 16;         // ranks of one box
@@ -745,7 +746,7 @@ k_bucket_scan_rows(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t n_nod
             for (int k = 0; k < 8; ++k) if (b0 + k * 32 + lane < blockIdx.x) base += (uint32_t)v[k];
         }
         base = __reduce_add_sync(FULLMASK, base);
-        if (dead && lane == 0) err.set(ERR_PEER_TIMEOUT);
+        if (dead && lane == 0) err.set(ERR_DEVICE_WAIT);
         if (n < nb) claim_off[n] = base + x - total;
         if (blockIdx.x == gridDim.x - 1 && lane == 31) claim_off[nb] = base + agg;
     }
@@ -1068,7 +1069,7 @@ k_shard_compact(const ShardArgs a) {
             if (m2) break;
             look -= 32;
         }
-        if (dead && lane == 0) a.err.set(ERR_PEER_TIMEOUT);
+        if (dead && lane == 0) a.err.set(ERR_DEVICE_WAIT);
         if (lane == 0) {
             if (tile) atomicExch(&st[tile], sc_pack(a.epoch, 2u, ec + tc, es + ts));
             pre_c = ec; pre_s = es;
@@ -1184,7 +1185,7 @@ __device__ __forceinline__ void shard_tile_flat(const ShardArgs& a, const uint32
             }
         }
         ec = __reduce_add_sync(FULLMASK, ec); es = __reduce_add_sync(FULLMASK, es);
-        if (dead && lane == 0) a.err.set(ERR_PEER_TIMEOUT);
+        if (dead && lane == 0) a.err.set(ERR_DEVICE_WAIT);
         if (lane == 0) {
             pre_c = ec;
             if (tile == a.n_tiles - 1) {
@@ -1959,7 +1960,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t* gbar, uint32_t n_cta, con
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gbar + 1) : "memory");
                 if (v != gen) break;
-                if (clock64() - t0 > 400000000ll) { err.set(ERR_PEER_TIMEOUT); break; }
+                if (clock64() - t0 > 400000000ll) { err.set(ERR_DEVICE_WAIT); break; }
             } while (true);
         }
     }
