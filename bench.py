@@ -364,9 +364,14 @@ def run_ours(args):
     def step_e2e():
         if world == 1:
             ctx.allocate_raw(pin_c.ptr, n_claim, None, pin_o.ptr, n_out, F)      # the bare C-ABI call
-        else:
+        elif args.e2e_copy:
             d_claims.copy_(h_claims_t, non_blocking=True)
             step_dev()
+            ctx.gather_read(pin_o.array)
+        else:
+            # the sharded call takes the pinned host buffer itself: the compaction kernel reads every claim exactly once, straight
+            # over PCIe (no copy-engine transfer in front of it); the table comes back with dra_gather_read
+            ctx.allocate_global_device(pin_c.ptr, n_claim, None, n_out, F)
             ctx.gather_read(pin_o.array)
 
     for _ in range(max(3, args.warmup)):
@@ -407,7 +412,10 @@ def run_ours(args):
                                     "mapped host memory and spins on the completion word; the kernel reads the claims from / writes the OutRecs to the pinned host buffers"
                                     if world == 1 and not args.no_direct and not args.no_resident else
                                     "direct: one cooperative launch, the kernel reads the claims from / writes the OutRecs to the pinned host buffers"
-                                    if world == 1 and not args.no_direct else "copy engine: H2D of the global claim array, kernels, D2H of the whole table")},
+                                    if world == 1 and not args.no_direct else
+                                    "copy engine: H2D of the global claim array, kernels, D2H of the whole table" if args.e2e_copy else
+                                    "the compaction kernel reads the global claim array from the pinned host buffer itself (zero-copy ingest), kernels, "
+                                    "D2H of the whole table (dra_gather_read)")},
                 "gpu_launches": launches,
                 "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "kernel": {"fused": "k_fused", "pack": "k_pack", "bucket_hist": "k_bucket_hist",
@@ -531,6 +539,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="e2e leg: enqueue H2D / kernel / D2H separately instead of one CUDA graph")
     ap.add_argument("--no-resident", action="store_true", help="e2e leg: one cooperative launch per batch instead of the resident kernel + doorbell")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (skip the other configs / calls)")
+    ap.add_argument("--e2e-copy", action="store_true", help="N > 1, e2e leg: H2D copy of the global claim array in front of the call instead of zero-copy ingest")
     ap.add_argument("--align", action="store_true", help="N > 1: device-side rendezvous of the ranks (dra_peer_rendezvous_device) between the untimed L2 "
                     "flush and the timed step; measured at N = 2: no difference (29.46 vs 29.48 us), off by default")
     args = ap.parse_args()

@@ -323,7 +323,8 @@ int  dra_peer_rendezvous_device(dra_ctx* ctx);
  *   result: dra_gather_table / dra_gather_read (n_out records, input order, global GPU indices)
  * out_off must tile [0, n_out) (slots no claim owns keep their previous contents).  flags: DRA_F_FRESH_INVENTORY.
  * With world == 1 no export is needed (the table is local).  A rank's live inventory is authoritative for its own
- * node range only. */
+ * node range only.  d_claims may also be a pinned host buffer (dra_host_alloc): the compaction kernel reads every claim
+ * exactly once, so it then ingests the batch over PCIe itself — no copy-engine transfer in front of the call. */
 int  dra_set_shard(dra_ctx* ctx, uint32_t node_lo, uint32_t node_hi, int take_stray);
 /* The whole partition: rank r serves nodes [bounds[r], bounds[r+1]) (bounds has world+1 entries, bounds[world] = n_node),
  * stray_rank answers claims naming no node.  Since every rank reads the whole claim array, it then also COUNTS what every
