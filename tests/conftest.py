@@ -36,7 +36,7 @@ def load_golden(name):
 
 
 GOLDEN_CASES = ["gpu_test4", "cfg1", "cfg2_small", "cfg4_small", "cfg5_small", "mixed0", "mixed1", "mixed2",
-                "mixed3", "mixed11_valid", "homog_w8", "homog_w32", "homog_16slice"]
+                "mixed3", "mixed11_valid", "homog_w8", "homog_w32", "homog_16slice", "b200_table"]
 
 
 @pytest.fixture(scope="session", params=["auto", "copy-engine", "bucket+pack"])

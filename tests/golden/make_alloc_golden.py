@@ -50,8 +50,30 @@ def cases():
     w = S.homog(1200, 6, 4, wide16=True, max_width=32); w.name = "homog_16slice"; yield w
 
 
+def b200_table(n_claim=420, n_node=8, seed=3):
+    """Every MIG profile a real B200 offers (tests/golden/b200_gi_profiles.json: NVML's answers, recorded on the GPU box), on
+    nodes of 8 such GPUs, a quarter of them with slices 2-3 taken."""
+    import json
+    doc = json.load(open(os.path.join(HERE, "b200_gi_profiles.json")))
+    t = R.default_table()
+    for p, (size, mask) in enumerate(doc["row"]):
+        t[15, p] = (size, 0, mask)
+    g, off = R.make_inventory([8] * n_node, model=15, mem_free_mib=183359)
+    r = S.splitmix64(0xB200 + seed, 3 * n_claim)
+    offered = np.array([p for p, (size, _) in enumerate(doc["row"]) if size], dtype=np.uint8)
+    c = np.zeros(n_claim, dtype=R.CLAIM_DTYPE)
+    c["kind"], c["count"] = R.KIND_MIG, 1
+    c["profile"] = offered[(r[0::3] % np.uint64(len(offered))).astype(np.int64)]
+    c["node"] = (r[1::3] % np.uint64(n_node)).astype(np.uint32)
+    g["busy"][(r[2::3][: len(g)] % np.uint64(4) == 0)] = 0b1100
+    return S.Workload("b200_table", g, off, t, c).finish()
+
+
 def main():
-    for w in cases():
+    only = set(sys.argv[1:])                 # e.g. `make_alloc_golden.py b200_table`: (re)generate just these cases
+    for w in list(cases()) + [b200_table()]:
+        if only and w.name not in only:
+            continue
         out, after = O.allocate(w.gpus, w.node_off, w.table, w.claims, w.out_off, w.n_out)
         path = os.path.join(HERE, f"alloc_{w.name}.npz")
         np.savez_compressed(path, gpus=w.gpus, node_off=w.node_off, table=w.table, claims=w.claims,
