@@ -213,3 +213,72 @@ func (c *Context) DeallocateBatch(claims []ClaimRec, outOff []uint32, out []OutR
 	}
 	return nil
 }
+
+// ---- one global batch over the GPUs of a box (one Context per GPU of ONE process) --------------------------------------
+// Set-up once, like the inventory: every context loads the WHOLE inventory, then
+//   ctx[r].CommInitLocal(r, world); ctx[r].SetShardMap(bounds, strayRank); ctx[r].ShardExport(nOutMax);
+//   ctx[r].PeerImportLocal(ctxs)
+// Per batch: AllocateBatchGlobal on every context (same claims, without waiting for each other), then GatherRead on the one
+// whose table is wanted.  The host does no partitioning and no merging (INTEGRATION.md §4).
+
+func (c *Context) CommInitLocal(rank, world int) error {
+	if rc := C.dra_comm_init_local(c.h, C.int(rank), C.int(world)); rc != 0 {
+		return lastError(c.h)
+	}
+	return nil
+}
+
+// SetShardMap: rank r serves nodes [bounds[r], bounds[r+1]); len(bounds) == world+1.
+func (c *Context) SetShardMap(bounds []uint32, strayRank int) error {
+	if rc := C.dra_set_shard_map(c.h, (*C.uint32_t)(unsafe.Pointer(&bounds[0])), C.int(strayRank)); rc != 0 {
+		return lastError(c.h)
+	}
+	return nil
+}
+
+func (c *Context) ShardExport(nOutMax uint32) error {
+	if rc := C.dra_shard_export(c.h, C.uint32_t(nOutMax), 0, nil); rc != 0 {
+		return lastError(c.h)
+	}
+	return nil
+}
+
+func (c *Context) PeerImportLocal(ctxs []*Context) error {
+	hs := make([]*C.dra_ctx, len(ctxs))
+	for i, o := range ctxs {
+		hs[i] = o.h
+	}
+	if rc := C.dra_peer_import_local(c.h, (**C.dra_ctx)(unsafe.Pointer(&hs[0]))); rc != 0 {
+		return lastError(c.h)
+	}
+	return nil
+}
+
+// AllocateBatchGlobal: claims must live in memory from dra_host_alloc (pinned): the device-side range filter then reads them
+// over PCIe itself.  Returns at once; GatherRead synchronises.
+func (c *Context) AllocateBatchGlobal(pinnedClaims unsafe.Pointer, nClaim int, nOut int, flags uint32) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	rc := C.dra_allocate_batch_global_device(c.h, (*C.dra_claim_rec)(pinnedClaims), C.uint32_t(nClaim), nil, C.uint32_t(nOut), C.uint32_t(flags))
+	if rc != 0 {
+		return lastError(c.h)
+	}
+	return nil
+}
+
+func (c *Context) GatherRead(out []OutRec) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	if rc := C.dra_gather_read(c.h, (*C.dra_out_rec)(unsafe.Pointer(&out[0])), C.uint32_t(len(out))); rc != 0 {
+		return lastError(c.h)
+	}
+	return nil
+}
+
+// PeerRendezvous lines the contexts' streams up on the device (optional; dra_peer_rendezvous_device).
+func (c *Context) PeerRendezvous() error {
+	if rc := C.dra_peer_rendezvous_device(c.h); rc != 0 {
+		return lastError(c.h)
+	}
+	return nil
+}
